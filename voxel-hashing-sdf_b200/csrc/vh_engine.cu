@@ -1,0 +1,879 @@
+// vh_engine.cu — host side of the engine and the C ABI of include/vh_c.h.
+//
+// Orchestration replaces GpuTsdfGenerator::processFrame (/root/reference/src/tsdf.cu:1485-1598), which per frame
+// builds and destroys two hash tables, performs ~20 blocking copies and 17 cudaMalloc/cudaFree pairs. Here a frame is:
+// two async H2D copies on an upload stream (double-buffered, overlapping the previous frame's kernels), one 64-byte
+// counter reset, and three kernel launches (allocate, integrate, marching cubes) on the compute stream. Nothing is
+// allocated, freed or synchronised per frame unless the caller asks for the synchronous entry point.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "vh_engine.h"
+
+using namespace vh;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+extern "C" int vh_set_error_(int code, const char* msg) { g_err = msg ? msg : ""; return code; }
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
+    if (_e != cudaSuccess) return fail(VH_ERR_CUDA, "CUDA Error: %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #call); \
+  } while (0)
+
+struct vh_engine {
+  vh_params P;
+  StaticParams S;
+  FrameParams F;
+  DeviceView D;
+  int num_sms = 148;
+  uint32_t capacity = 0;
+  cudaStream_t stream = nullptr, upload = nullptr;
+  float* d_depth[2] = {nullptr, nullptr};
+  uint8_t* d_rgb[2] = {nullptr, nullptr};
+  cudaEvent_t ev_uploaded[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  bool buf_used[2] = {false, false};
+  int ring = 0;
+  const float* cur_depth = nullptr;     // device pointers the stage calls operate on
+  const uint8_t* cur_rgb = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // pinned read-back block: counters of the last frame + flags
+  struct HostBlock { FrameCounters c; int map_error; int engine_error; int heap_counter; int pad; unsigned long long arena_top; };
+  HostBlock* h_block = nullptr;
+  int* d_flags = nullptr;               // [0] map error, [1] engine error
+  uint64_t frames = 0, updates_total = 0;
+  uint64_t max_tris_per_frame = 0, known_arena_top = 0;
+  int frames_in_flight = 0;
+  // full-map extraction scratch
+  int* d_full_list = nullptr; int* d_full_count = nullptr; unsigned long long* d_full_off = nullptr; int* d_full_cnt = nullptr;
+  u64* d_keys_tmp = nullptr; size_t keys_tmp_cap = 0;
+  std::mutex mtx;
+};
+
+// ---- frame constants on the host: getFrustumCenter / streamInCPU2GPU preamble (tsdf.cu:154-161, :197-206, :300-312)
+// compiled with -ffp-contract=off: plain float expressions in the reference's order
+static void host_pixel_to_world(const vh_params& P, const float* c2w, int px, int py, float z, float out[3]) {
+  const float x = ((float)px - P.cx) * z / P.fx;
+  const float y = ((float)py - P.cy) * z / P.fy;
+  out[0] = x * c2w[0] + y * c2w[1] + z * c2w[2] + c2w[3];
+  out[1] = x * c2w[4] + y * c2w[5] + z * c2w[6] + c2w[7];
+  out[2] = x * c2w[8] + y * c2w[9] + z * c2w[10] + c2w[11];
+}
+
+static void setup_frame(vh_engine* e, const float* c2w) {
+  FrameParams& F = e->F;
+  const vh_params& P = e->P;
+  memcpy(F.c2w, c2w, sizeof(F.c2w));
+  host_pixel_to_world(P, c2w, P.width / 2, P.height / 2, P.max_depth / 2, F.fc);
+  const float cs = e->S.chunk_size;
+  const int rng = (int)std::ceil((double)P.chunk_radius / (double)cs);
+  const int lo = P.max_chunk_num ? -P.max_chunk_num / 2 : INT32_MIN / 2;
+  const int hi = P.max_chunk_num ? P.max_chunk_num / 2 - 1 : INT32_MAX / 2;
+  for (int a = 0; a < 3; a++) {
+    const int cc = (int)floorf(F.fc[a] / cs);
+    F.cstart[a] = std::max(cc - rng, lo);
+    F.cend[a] = std::min(cc + rng, hi);
+  }
+  F.chunk_test_radius = (float)((double)0.5f * (double)P.chunk_radius * (double)sqrtf(3.0f) * 1.1);
+  F.frame = (uint32_t)(++e->frames);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* vh_last_error(void) { return g_err.c_str(); }
+const char* vh_version(void) { return "vhsdf-b200 0.1 (sm_100a)"; }
+
+int vh_default_params(vh_params* p) {
+  if (!p) return fail(VH_ERR_INVALID, "null params");
+  memset(p, 0, sizeof(*p));
+  p->width = 640; p->height = 480;
+  p->fx = p->fy = 577.0f; p->cx = 320.0f; p->cy = 240.0f;        // scene0220_02.yaml:11-14
+  p->min_depth = 0.1f; p->max_depth = 10.0f;
+  p->vox_size = 0.01f; p->trunc_margin = 0.05f;
+  p->voxels_per_block = 8; p->blocks_per_chunk = 8;
+  p->dda_stride = 10; p->max_ray_steps = 100;
+  p->chunk_radius = 4.0f; p->max_chunk_num = 128;
+  p->num_buckets = 1 << 20; p->entries_per_bucket = 4;
+  p->pool_blocks = 1 << 20;
+  p->use_color = 1; p->mc_per_frame = 1;
+  p->device = 0; p->shard_rank = 0; p->shard_count = 1;
+  p->depth_tile_smem = 1;
+  p->tri_arena_bytes = 0;
+  return VH_OK;
+}
+
+static int free_engine(vh_engine* e) {
+  if (!e) return VH_OK;
+  cudaSetDevice(e->P.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->upload) cudaStreamSynchronize(e->upload);
+  DeviceView& D = e->D;
+  cudaFree(D.map.keys); cudaFree(D.map.slots); cudaFree(D.map.free_list); cudaFree(D.map.free_top); cudaFree(D.map.key_heap);
+  cudaFree(D.map.heap_counter); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.visible);
+  cudaFree(D.counters); cudaFree(D.arena); cudaFree(D.arena_top); cudaFree(D.tri_offset); cudaFree(D.tri_count); cudaFree(e->d_flags);
+  cudaFree(e->d_full_list); cudaFree(e->d_full_count); cudaFree(e->d_full_off); cudaFree(e->d_full_cnt); cudaFree(e->d_keys_tmp);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(e->d_depth[i]); cudaFree(e->d_rgb[i]);
+    if (e->ev_uploaded[i]) cudaEventDestroy(e->ev_uploaded[i]);
+    if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
+  }
+  for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->h_block) cudaFreeHost(e->h_block);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->upload) cudaStreamDestroy(e->upload);
+  delete e;
+  return VH_OK;
+}
+
+__global__ void init_free_list_kernel(int* free_list, int n) {
+  // slot s is handed out in ascending order: the stack top holds slot 0
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) free_list[i] = n - 1 - i;
+}
+
+static int reset_map(vh_engine* e) {
+  DeviceView& D = e->D;
+  const int nb = e->P.pool_blocks;
+  CK(cudaMemsetAsync(D.map.keys, 0xFF, (size_t)e->capacity * sizeof(u64), e->stream));
+  CK(cudaMemsetAsync(D.map.slots, 0xFF, (size_t)e->capacity * sizeof(int), e->stream));
+  CK(cudaMemsetAsync(D.stamps, 0, (size_t)e->capacity * sizeof(uint32_t), e->stream));
+  CK(cudaMemsetAsync(D.sdf, 0, (size_t)nb * BLOCK_VOX * sizeof(float), e->stream));      // Voxel(): sdf = 0, weight = 0 (tsdf.cuh:126-128)
+  CK(cudaMemsetAsync(D.wgt, 0, (size_t)nb * BLOCK_VOX * sizeof(float), e->stream));
+  if (D.rgb) CK(cudaMemsetAsync(D.rgb, 0, (size_t)nb * BLOCK_VOX * sizeof(uchar4), e->stream));
+  CK(cudaMemsetAsync(D.tri_offset, 0, (size_t)nb * sizeof(unsigned long long), e->stream));
+  CK(cudaMemsetAsync(D.tri_count, 0, (size_t)nb * sizeof(int), e->stream));
+  CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
+  CK(cudaMemsetAsync(D.arena_top, 0, sizeof(unsigned long long), e->stream));
+  CK(cudaMemsetAsync(D.map.heap_counter, 0, sizeof(int), e->stream));
+  CK(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
+  init_free_list_kernel<<<(nb + 255) / 256, 256, 0, e->stream>>>(D.map.free_list, nb);
+  CK(cudaMemcpyAsync(D.map.free_top, &nb, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0;
+  memset(e->h_block, 0, sizeof(*e->h_block));
+  return VH_OK;
+}
+
+int vh_create(const vh_params* p, vh_engine** out) {
+  if (!p || !out) return fail(VH_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (p->voxels_per_block != VPB) return fail(VH_ERR_INVALID, "voxels_per_block must be %d (got %d)", VPB, p->voxels_per_block);
+  if (p->width <= 0 || p->height <= 0 || p->vox_size <= 0 || p->trunc_margin <= 0 || p->dda_stride <= 0 || p->max_ray_steps <= 0 ||
+      p->blocks_per_chunk <= 0 || p->num_buckets <= 0 || p->entries_per_bucket <= 0 || p->pool_blocks <= 0 || p->shard_count <= 0 ||
+      p->shard_rank < 0 || p->shard_rank >= p->shard_count)
+    return fail(VH_ERR_INVALID, "invalid parameter value");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(VH_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (p->device < 0 || p->device >= ndev) return fail(VH_ERR_INVALID, "device %d out of range (%d devices)", p->device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, p->device));
+  if (prop.major != 10) return fail(VH_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200) only", p->device, prop.major, prop.minor);
+  CK(cudaSetDevice(p->device));
+
+  vh_engine* e = new vh_engine;
+  e->P = *p;
+  e->num_sms = prop.multiProcessorCount;
+  StaticParams& S = e->S;
+  S.W = p->width; S.H = p->height; S.fx = p->fx; S.fy = p->fy; S.cx = p->cx; S.cy = p->cy;
+  S.min_depth = p->min_depth; S.max_depth = p->max_depth; S.vox_size = p->vox_size; S.trunc = p->trunc_margin;
+  S.block_size = (float)VPB * p->vox_size;                                          // tsdf.cu:1326
+  S.chunk_size = (float)(p->blocks_per_chunk * VPB) * p->vox_size;                  // tsdf.cu:1271
+  S.half_vox = 0.5f * p->vox_size;
+  S.stride = p->dda_stride; S.max_steps = p->max_ray_steps; S.bpc = p->blocks_per_chunk;
+  const int T = 8;                                                                  // T_PER_BLOCK launch shape, tsdf.cu:2263-2264
+  const int gx = (p->width / p->dda_stride + T - 1) / T * T, gy = (p->height / p->dda_stride + T - 1) / T * T;
+  S.nrx = std::min(gx, (p->width + p->dda_stride - 1) / p->dda_stride);
+  S.nry = std::min(gy, (p->height + p->dda_stride - 1) / p->dda_stride);
+  S.use_color = p->use_color ? 1 : 0;
+  S.shard_rank = (uint32_t)p->shard_rank; S.shard_count = (uint32_t)p->shard_count;
+
+  uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket;
+  uint64_t cap = 1024;
+  while (cap < want) cap <<= 1;
+  if (cap > (1ull << 31)) { delete e; return fail(VH_ERR_INVALID, "hash table too large"); }
+  e->capacity = (uint32_t)cap;
+
+  DeviceView& D = e->D;
+  memset(&D, 0, sizeof(D));
+  const size_t nb = (size_t)p->pool_blocks;
+  const size_t rays = (size_t)S.nrx * S.nry;
+  D.list_cap = (int)std::max(rays * (size_t)S.max_steps, nb);
+  uint64_t arena_bytes = p->tri_arena_bytes ? p->tri_arena_bytes : (1ull << 30);
+  D.arena_cap = arena_bytes / sizeof(vh_triangle);
+#define ALLOC(ptr, bytes)                                                                                           \
+  do {                                                                                                              \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                                           \
+    if (_e != cudaSuccess) { int rc = fail(VH_ERR_CUDA, "CUDA Error: cudaMalloc(%zu bytes) for %s: %s", (size_t)(bytes), #ptr, cudaGetErrorString(_e)); free_engine(e); return rc; } \
+  } while (0)
+  ALLOC(D.map.keys, cap * sizeof(u64));
+  ALLOC(D.map.slots, cap * sizeof(int));
+  ALLOC(D.stamps, cap * sizeof(uint32_t));
+  ALLOC(D.map.free_list, nb * sizeof(int));
+  ALLOC(D.map.free_top, sizeof(int));
+  ALLOC(D.map.key_heap, nb * sizeof(u64));
+  ALLOC(D.map.heap_counter, sizeof(int));
+  ALLOC(e->d_flags, 2 * sizeof(int));
+  ALLOC(D.sdf, nb * BLOCK_VOX * sizeof(float));
+  ALLOC(D.wgt, nb * BLOCK_VOX * sizeof(float));
+  if (S.use_color) ALLOC(D.rgb, nb * BLOCK_VOX * sizeof(uchar4));
+  ALLOC(D.visible, (size_t)D.list_cap * sizeof(int));
+  ALLOC(D.counters, sizeof(FrameCounters));
+  ALLOC(D.arena, D.arena_cap * sizeof(vh_triangle));
+  ALLOC(D.arena_top, sizeof(unsigned long long));
+  ALLOC(D.tri_offset, nb * sizeof(unsigned long long));
+  ALLOC(D.tri_count, nb * sizeof(int));
+  const size_t npx = (size_t)p->width * p->height;
+  for (int i = 0; i < 2; i++) {
+    ALLOC(e->d_depth[i], npx * sizeof(float));
+    ALLOC(e->d_rgb[i], npx * 3);
+  }
+#undef ALLOC
+  D.map.mask = e->capacity - 1;
+  D.map.num_blocks = p->pool_blocks;
+  D.map.error_flag = e->d_flags;
+  D.engine_error = e->d_flags + 1;
+  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&e->upload, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaHostAlloc((void**)&e->h_block, sizeof(*e->h_block), cudaHostAllocDefault) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; i++)
+    ok = cudaEventCreateWithFlags(&e->ev_uploaded[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
+  if (!ok) { free_engine(e); return fail(VH_ERR_CUDA, "CUDA Error: stream/event creation failed"); }
+  upload_mc_tables();
+  int rc = reset_map(e);
+  if (rc != VH_OK) { free_engine(e); return rc; }
+  e->cur_depth = e->d_depth[0]; e->cur_rgb = e->d_rgb[0];
+  *out = e;
+  return VH_OK;
+}
+
+int vh_destroy(vh_engine* e) { return free_engine(e); }
+
+int vh_reset(vh_engine* e) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  return reset_map(e);
+}
+
+// ---- triangle arena maintenance -----------------------------------------------------------------
+__global__ void compact_copy_kernel(const vh_triangle* __restrict__ src, vh_triangle* __restrict__ dst, const unsigned long long* __restrict__ old_off,
+                                    const unsigned long long* __restrict__ new_off, const int* __restrict__ cnt, int n) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n || cnt[w] <= 0) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + old_off[w]);
+  uint4* d = reinterpret_cast<uint4*>(dst + new_off[w]);
+  for (int i = lane; i < cnt[w] * 3; i += 32) d[i] = s[i];
+}
+__global__ void widen_counts_kernel(const int* cnt, unsigned long long* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cnt[i] > 0 ? (unsigned long long)cnt[i] : 0ull;
+}
+
+// Drop superseded triangles (blocks re-meshed in later frames) and make room for `need` more. Stream must be idle.
+static int compact_arena(vh_engine* e, unsigned long long need) {
+  DeviceView& D = e->D;
+  const int nb = e->P.pool_blocks;
+  unsigned long long *d_wide = nullptr, *d_new = nullptr;
+  void* d_tmp = nullptr; size_t tmp_bytes = 0;
+  CK(cudaMalloc(&d_wide, (size_t)nb * sizeof(unsigned long long)));
+  CK(cudaMalloc(&d_new, ((size_t)nb + 1) * sizeof(unsigned long long)));
+  widen_counts_kernel<<<(nb + 255) / 256, 256, 0, e->stream>>>(D.tri_count, d_wide, nb);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_new, nb, e->stream);
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wide, d_new, nb, e->stream);
+  unsigned long long last_off = 0, last_cnt = 0;
+  CK(cudaMemcpyAsync(&last_off, d_new + nb - 1, sizeof(last_off), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(&last_cnt, d_wide + nb - 1, sizeof(last_cnt), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const unsigned long long live = last_off + last_cnt;
+  unsigned long long new_cap = D.arena_cap;
+  while (live + need > new_cap / 2) new_cap *= 2;      // keep at least half the arena free after compaction
+  vh_triangle* fresh = nullptr;
+  cudaError_t ce = cudaMalloc((void**)&fresh, new_cap * sizeof(vh_triangle));
+  if (ce != cudaSuccess) { cudaFree(d_wide); cudaFree(d_new); cudaFree(d_tmp); return fail(VH_ERR_ARENA_FULL, "triangle arena cannot grow to %llu triangles: %s", new_cap, cudaGetErrorString(ce)); }
+  compact_copy_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(D.arena, fresh, D.tri_offset, d_new, D.tri_count, nb);
+  CK(cudaMemcpyAsync(D.tri_offset, d_new, (size_t)nb * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(D.arena_top, &live, sizeof(live), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(D.arena); cudaFree(d_wide); cudaFree(d_new); cudaFree(d_tmp);
+  D.arena = fresh; D.arena_cap = new_cap;
+  e->known_arena_top = live;
+  return VH_OK;
+}
+
+// ---- frame pipeline -----------------------------------------------------------------------------
+static int enqueue_stages(vh_engine* e, bool do_alloc) {
+  DeviceView& D = e->D;
+  if (do_alloc) {
+    CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
+    launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
+  }
+  CK(cudaEventRecord(e->ev[2], e->stream));
+  launch_integrate(e->S, e->F, e->cur_depth, e->cur_rgb, D, e->num_sms, e->stream);
+  CK(cudaEventRecord(e->ev[3], e->stream));
+  if (e->P.mc_per_frame)
+    launch_marching_cubes(e->S, e->F, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, e->num_sms, e->stream);
+  CK(cudaEventRecord(e->ev[4], e->stream));
+  return VH_OK;
+}
+
+static int enqueue_readback(vh_engine* e) {
+  DeviceView& D = e->D;
+  CK(cudaMemcpyAsync(&e->h_block->c, D.counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(&e->h_block->map_error, e->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(&e->h_block->heap_counter, D.map.heap_counter, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(&e->h_block->arena_top, D.arena_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  return VH_OK;
+}
+
+// after a sync: fold the read-back block into host state, surface device-side errors, repair arena overflow
+static int finish_sync(vh_engine* e) {
+  auto* hb = e->h_block;
+  e->frames_in_flight = 0;
+  e->known_arena_top = hb->arena_top;
+  e->max_tris_per_frame = std::max<uint64_t>(e->max_tris_per_frame, hb->c.triangles);
+  if (hb->map_error & MAP_TABLE_FULL) return fail(VH_ERR_TABLE_FULL, "hash table full (%u entries): raise num_buckets/entries_per_bucket", e->capacity);
+  if (hb->map_error & MAP_POOL_FULL) return fail(VH_ERR_POOL_FULL, "out of block memory: pool of %d voxel blocks exhausted, raise pool_blocks", e->P.pool_blocks);
+  if (hb->engine_error & 1) {
+    // the last frame's marching cubes ran out of arena: compact/grow, then redo it (it only reads voxels + stamps)
+    int zero = 0;
+    CK(cudaMemcpyAsync(e->D.engine_error, &zero, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    int rc = compact_arena(e, std::max<unsigned long long>(hb->c.triangles * 2, 1ull << 20));
+    if (rc != VH_OK) return rc;
+    CK(cudaMemsetAsync(&e->D.counters->triangles, 0, sizeof(unsigned long long), e->stream));
+    launch_marching_cubes(e->S, e->F, e->D, e->D.visible, &e->D.counters->visible_count, 0, e->D.tri_offset, e->D.tri_count, e->num_sms, e->stream);
+    rc = enqueue_readback(e);
+    if (rc != VH_OK) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    if (hb->engine_error & 1) return fail(VH_ERR_ARENA_FULL, "triangle arena overflow persists after growth");
+    e->known_arena_top = hb->arena_top;
+  }
+  return VH_OK;
+}
+
+// keep enough arena head-room for the frames that will be in flight before the next sync
+static int make_room(vh_engine* e) {
+  if (!e->P.mc_per_frame) return VH_OK;
+  const unsigned long long per_frame = std::max<unsigned long long>(e->max_tris_per_frame * 2, 1ull << 18);
+  const unsigned long long projected = e->known_arena_top + per_frame * (unsigned long long)(e->frames_in_flight + 2);
+  if (projected <= e->D.arena_cap) return VH_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  int rc = finish_sync(e);
+  if (rc != VH_OK) return rc;
+  if (e->known_arena_top + per_frame * 2 <= e->D.arena_cap) return VH_OK;
+  return compact_arena(e, per_frame * 2);
+}
+
+static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w, bool host_inputs) {
+  if (!e || !depth || !c2w) return fail(VH_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->P.device));
+  int rc = make_room(e);
+  if (rc != VH_OK) return rc;
+  const size_t npx = (size_t)e->P.width * e->P.height;
+  CK(cudaEventRecord(e->ev[0], e->stream));
+  if (host_inputs) {
+    const int b = e->ring & 1; e->ring++;
+    if (e->buf_used[b]) CK(cudaStreamWaitEvent(e->upload, e->ev_consumed[b], 0));     // previous reader of this buffer is done
+    CK(cudaMemcpyAsync(e->d_depth[b], depth, npx * sizeof(float), cudaMemcpyHostToDevice, e->upload));
+    if (rgb && e->S.use_color) CK(cudaMemcpyAsync(e->d_rgb[b], rgb, npx * 3, cudaMemcpyHostToDevice, e->upload));
+    CK(cudaEventRecord(e->ev_uploaded[b], e->upload));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_uploaded[b], 0));
+    e->cur_depth = e->d_depth[b];
+    e->cur_rgb = (rgb && e->S.use_color) ? e->d_rgb[b] : nullptr;
+    e->buf_used[b] = true;
+    CK(cudaEventRecord(e->ev[1], e->stream));
+    setup_frame(e, c2w);
+    const int keep = e->S.use_color;   // colour only when the caller supplied an image
+    e->S.use_color = e->cur_rgb ? keep : 0;
+    rc = enqueue_stages(e, true);
+    e->S.use_color = keep;
+    if (rc != VH_OK) return rc;
+    CK(cudaEventRecord(e->ev_consumed[b], e->stream));
+  } else {
+    e->cur_depth = depth;
+    e->cur_rgb = e->S.use_color ? rgb : nullptr;
+    CK(cudaEventRecord(e->ev[1], e->stream));
+    setup_frame(e, c2w);
+    const int keep = e->S.use_color;
+    e->S.use_color = e->cur_rgb ? keep : 0;
+    rc = enqueue_stages(e, true);
+    e->S.use_color = keep;
+    if (rc != VH_OK) return rc;
+  }
+  e->frames_in_flight++;
+  return enqueue_readback(e);
+}
+
+int vh_integrate_async(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  return integrate_common(e, depth, rgb, c2w, true);
+}
+
+int vh_integrate_device(vh_engine* e, const float* d_depth, const uint8_t* d_rgb, const float* c2w) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  return integrate_common(e, d_depth, d_rgb, c2w, false);
+}
+
+int vh_wait_uploads(vh_engine* e) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->upload));
+  return VH_OK;
+}
+
+int vh_sync(vh_engine* e) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_sync(e);
+}
+
+int vh_integrate(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  int rc = integrate_common(e, depth, rgb, c2w, true);
+  if (rc != VH_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_sync(e);
+}
+
+// ---- stage entry points ---------------------------------------------------------------------------
+int vh_upload_frame(vh_engine* e, const float* depth, const uint8_t* rgb) {
+  if (!e || !depth) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  const size_t npx = (size_t)e->P.width * e->P.height;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(e->d_depth[0], depth, npx * sizeof(float), cudaMemcpyHostToDevice));
+  if (rgb) CK(cudaMemcpy(e->d_rgb[0], rgb, npx * 3, cudaMemcpyHostToDevice));
+  e->cur_depth = e->d_depth[0];
+  e->cur_rgb = (rgb && e->S.use_color) ? e->d_rgb[0] : nullptr;
+  return VH_OK;
+}
+
+int vh_stage_allocate(vh_engine* e, const float* d_depth, const float* c2w) {
+  if (!e || !c2w) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  if (d_depth) e->cur_depth = d_depth;
+  setup_frame(e, c2w);
+  CK(cudaMemsetAsync(e->D.counters, 0, sizeof(FrameCounters), e->stream));
+  launch_alloc_visible(e->S, e->F, e->cur_depth, e->D, e->stream);
+  int rc = enqueue_readback(e);
+  if (rc != VH_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_sync(e);
+}
+
+int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  if (d_depth) e->cur_depth = d_depth;
+  if (d_rgb) e->cur_rgb = d_rgb;
+  const int keep = e->S.use_color;
+  e->S.use_color = e->cur_rgb ? keep : 0;
+  CK(cudaMemsetAsync(&e->D.counters->voxel_updates, 0, sizeof(unsigned long long), e->stream));
+  launch_integrate(e->S, e->F, e->cur_depth, e->cur_rgb, e->D, e->num_sms, e->stream);
+  e->S.use_color = keep;
+  int rc = enqueue_readback(e);
+  if (rc != VH_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_sync(e);
+}
+
+int vh_stage_marching_cubes(vh_engine* e) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  int rc = make_room(e);
+  if (rc != VH_OK) return rc;
+  CK(cudaMemsetAsync(&e->D.counters->triangles, 0, sizeof(unsigned long long), e->stream));
+  launch_marching_cubes(e->S, e->F, e->D, e->D.visible, &e->D.counters->visible_count, 0, e->D.tri_offset, e->D.tri_count, e->num_sms, e->stream);
+  rc = enqueue_readback(e);
+  if (rc != VH_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_sync(e);
+}
+
+static int upload_keys(vh_engine* e, const int32_t* keys_xyz, int n) {
+  if ((size_t)n > e->keys_tmp_cap) {
+    cudaFree(e->d_keys_tmp);
+    e->d_keys_tmp = nullptr;
+    CK(cudaMalloc((void**)&e->d_keys_tmp, (size_t)n * sizeof(u64)));
+    e->keys_tmp_cap = (size_t)n;
+  }
+  std::vector<u64> packed((size_t)n);
+  for (int i = 0; i < n; i++) {
+    const int x = keys_xyz[3 * i], y = keys_xyz[3 * i + 1], z = keys_xyz[3 * i + 2];
+    if (!key_in_range(x, y, z)) return fail(VH_ERR_INVALID, "block coordinate (%d,%d,%d) outside [-2^20, 2^20)", x, y, z);
+    packed[i] = pack_key(x, y, z);
+  }
+  CK(cudaMemcpyAsync(e->d_keys_tmp, packed.data(), (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return VH_OK;
+}
+
+int vh_set_visible(vh_engine* e, const int32_t* keys_xyz, int n, const float* c2w) {
+  if (!e || !c2w || (n > 0 && !keys_xyz)) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  if (n > e->D.list_cap) return fail(VH_ERR_INVALID, "visible list of %d blocks exceeds capacity %d", n, e->D.list_cap);
+  setup_frame(e, c2w);
+  CK(cudaMemsetAsync(e->D.counters, 0, sizeof(FrameCounters), e->stream));
+  if (n > 0) {
+    int rc = upload_keys(e, keys_xyz, n);
+    if (rc != VH_OK) return rc;
+    launch_set_visible(e->D, e->d_keys_tmp, n, e->F.frame, e->stream);
+  }
+  int rc = enqueue_readback(e);
+  if (rc != VH_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_sync(e);
+}
+
+int vh_get_stats(vh_engine* e, vh_stats* out) {
+  if (!e || !out) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  memset(out, 0, sizeof(*out));
+  out->frames = e->frames;
+  out->visible_blocks = (uint32_t)e->h_block->c.visible_count;
+  out->allocated_blocks = (uint32_t)e->h_block->heap_counter;
+  out->voxel_updates = e->h_block->c.voxel_updates;
+  out->voxel_updates_total = 0;
+  out->triangles = e->h_block->c.triangles;
+  out->arena_triangles = e->h_block->arena_top;
+  if (e->frames > 0) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) out->ms_upload = ms;
+    if (cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]) == cudaSuccess) out->ms_alloc = ms;
+    if (cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]) == cudaSuccess) out->ms_integrate = ms;
+    if (cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]) == cudaSuccess) out->ms_mc = ms;
+    cudaGetLastError();
+  }
+  return VH_OK;
+}
+
+void* vh_stream(vh_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+// ---- inspection -------------------------------------------------------------------------------------
+__global__ void entries_to_keys_kernel(const u64* __restrict__ table, const int* __restrict__ list, int n, u64* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = table[list[i]];
+}
+
+int vh_visible_keys(vh_engine* e, int32_t* out_xyz, int cap, int* n_out) {
+  if (!e || !n_out) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  int n = 0;
+  CK(cudaMemcpy(&n, &e->D.counters->visible_count, sizeof(int), cudaMemcpyDeviceToHost));
+  n = std::min(n, e->D.list_cap);
+  *n_out = n;
+  if (!out_xyz || n == 0) return VH_OK;
+  const int m = std::min(n, cap);
+  u64* d_tmp = nullptr;
+  CK(cudaMalloc((void**)&d_tmp, (size_t)m * sizeof(u64)));
+  entries_to_keys_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(e->D.map.keys, e->D.visible, m, d_tmp);
+  std::vector<u64> keys((size_t)m);
+  cudaError_t ce = cudaMemcpyAsync(keys.data(), d_tmp, (size_t)m * sizeof(u64), cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaFree(d_tmp);
+  CK(ce);
+  for (int i = 0; i < m; i++) unpack_key(keys[i], out_xyz[3 * i], out_xyz[3 * i + 1], out_xyz[3 * i + 2]);
+  return VH_OK;
+}
+
+int vh_allocated_keys(vh_engine* e, int32_t* out_xyz, int cap, int* n_out) {
+  if (!e || !n_out) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  int n = 0;
+  CK(cudaMemcpy(&n, e->D.map.heap_counter, sizeof(int), cudaMemcpyDeviceToHost));
+  n = std::min(n, e->P.pool_blocks);
+  *n_out = n;
+  if (!out_xyz || n == 0) return VH_OK;
+  const int m = std::min(n, cap);
+  std::vector<u64> keys((size_t)m);
+  CK(cudaMemcpy(keys.data(), e->D.map.key_heap, (size_t)m * sizeof(u64), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < m; i++) unpack_key(keys[i], out_xyz[3 * i], out_xyz[3 * i + 1], out_xyz[3 * i + 2]);
+  return VH_OK;
+}
+
+int vh_download_blocks(vh_engine* e, const int32_t* keys_xyz, int n, float* sdf, float* weight, uint8_t* rgb, uint8_t* found) {
+  if (!e || (n > 0 && !keys_xyz)) return fail(VH_ERR_INVALID, "null argument");
+  if (n <= 0) return VH_OK;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  const int CH = 16384;   // blocks per staging round (64 MB of planes)
+  float *d_s = nullptr, *d_w = nullptr; uint8_t *d_c = nullptr, *d_f = nullptr;
+  const int m0 = std::min(n, CH);
+  CK(cudaMalloc((void**)&d_s, (size_t)m0 * BLOCK_VOX * sizeof(float)));
+  CK(cudaMalloc((void**)&d_w, (size_t)m0 * BLOCK_VOX * sizeof(float)));
+  CK(cudaMalloc((void**)&d_c, (size_t)m0 * BLOCK_VOX * 3));
+  CK(cudaMalloc((void**)&d_f, (size_t)m0));
+  int rc = VH_OK;
+  for (int o = 0; o < n && rc == VH_OK; o += CH) {
+    const int m = std::min(CH, n - o);
+    rc = upload_keys(e, keys_xyz + 3 * (size_t)o, m);
+    if (rc != VH_OK) break;
+    launch_gather_blocks(e->D, e->d_keys_tmp, m, d_s, d_w, d_c, d_f, e->stream);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce == cudaSuccess && sdf) ce = cudaMemcpy(sdf + (size_t)o * BLOCK_VOX, d_s, (size_t)m * BLOCK_VOX * sizeof(float), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && weight) ce = cudaMemcpy(weight + (size_t)o * BLOCK_VOX, d_w, (size_t)m * BLOCK_VOX * sizeof(float), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && rgb) ce = cudaMemcpy(rgb + (size_t)o * BLOCK_VOX * 3, d_c, (size_t)m * BLOCK_VOX * 3, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && found) ce = cudaMemcpy(found + o, d_f, (size_t)m, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) rc = fail(VH_ERR_CUDA, "CUDA Error: %s in vh_download_blocks", cudaGetErrorString(ce));
+  }
+  cudaFree(d_s); cudaFree(d_w); cudaFree(d_c); cudaFree(d_f);
+  return rc;
+}
+
+int vh_voxel_checksum(vh_engine* e, double* sum_sdf, double* sum_w, uint64_t* n_observed, uint64_t* n_negative) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CK(cudaSetDevice(e->P.device));
+  double* d4 = nullptr;
+  CK(cudaMalloc((void**)&d4, 4 * sizeof(double)));
+  launch_checksum(e->D, d4, e->stream);
+  double h4[4];
+  cudaError_t ce = cudaMemcpyAsync(h4, d4, sizeof(h4), cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaFree(d4);
+  CK(ce);
+  if (sum_sdf) *sum_sdf = h4[0];
+  if (sum_w) *sum_w = h4[1];
+  if (n_observed) *n_observed = (uint64_t)h4[2];
+  if (n_negative) *n_negative = (uint64_t)h4[3];
+  return VH_OK;
+}
+
+// ---- mesh assembly ------------------------------------------------------------------------------------
+struct MeshBlocks {
+  std::vector<u64> key; std::vector<unsigned long long> off; std::vector<int> cnt;
+  const vh_triangle* arena = nullptr; vh_triangle* tmp_arena = nullptr;
+};
+
+static inline int floor_div(int a, int b) { return (int)floorf((float)a / (float)b); }   // block2chunk, tsdf.cu:256-260
+
+// collect (key, offset, count) records, sorted in tsdf2mesh order: chunk x,y,z ascending, then block-in-chunk linear
+static int collect_blocks(vh_engine* e, int mode, MeshBlocks& mb) {
+  DeviceView D = e->D;
+  const int nb = e->P.pool_blocks;
+  const unsigned long long* d_off = D.tri_offset; const int* d_cnt = D.tri_count;
+  mb.arena = D.arena;
+  if (mode == VH_MESH_FULL_MAP) {
+    if (!e->d_full_list) {
+      CK(cudaMalloc((void**)&e->d_full_list, (size_t)nb * sizeof(int)));
+      CK(cudaMalloc((void**)&e->d_full_count, sizeof(int)));
+      CK(cudaMalloc((void**)&e->d_full_off, (size_t)nb * sizeof(unsigned long long)));
+      CK(cudaMalloc((void**)&e->d_full_cnt, (size_t)nb * sizeof(int)));
+    }
+    // marching cubes over every allocated block into a scratch arena; grow until it fits
+    unsigned long long cap = std::max<unsigned long long>(1ull << 20, D.arena_cap / 4);
+    unsigned long long* d_top = nullptr;
+    CK(cudaMalloc((void**)&d_top, sizeof(unsigned long long)));
+    for (;;) {
+      CK(cudaMalloc((void**)&mb.tmp_arena, cap * sizeof(vh_triangle)));
+      DeviceView V = D;
+      V.arena = mb.tmp_arena; V.arena_cap = cap; V.arena_top = d_top; V.list_cap = nb;
+      CK(cudaMemsetAsync(d_top, 0, sizeof(unsigned long long), e->stream));
+      CK(cudaMemsetAsync(e->d_full_cnt, 0, (size_t)nb * sizeof(int), e->stream));
+      launch_list_all_blocks(D, e->d_full_list, e->d_full_count, e->stream);
+      launch_marching_cubes(e->S, e->F, V, e->d_full_list, e->d_full_count, 1, e->d_full_off, e->d_full_cnt, e->num_sms, e->stream);
+      unsigned long long top = 0; int err = 0, zero = 0;
+      CK(cudaMemcpyAsync(&top, d_top, sizeof(top), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaMemcpyAsync(&err, D.engine_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      if (!(err & 1)) break;
+      CK(cudaMemcpy(D.engine_error, &zero, sizeof(int), cudaMemcpyHostToDevice));
+      cudaFree(mb.tmp_arena); mb.tmp_arena = nullptr;
+      cap = std::max(cap * 2, top + (top >> 2));
+    }
+    cudaFree(d_top);
+    d_off = e->d_full_off; d_cnt = e->d_full_cnt; mb.arena = mb.tmp_arena;
+  }
+  u64* r_key = nullptr; unsigned long long* r_off = nullptr; int* r_cnt = nullptr; int* r_n = nullptr;
+  CK(cudaMalloc((void**)&r_key, (size_t)nb * sizeof(u64)));
+  CK(cudaMalloc((void**)&r_off, (size_t)nb * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&r_cnt, (size_t)nb * sizeof(int)));
+  CK(cudaMalloc((void**)&r_n, sizeof(int)));
+  launch_block_records(D, d_off, d_cnt, r_key, r_off, r_cnt, r_n, e->stream);
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, r_n, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  std::vector<u64> key((size_t)n); std::vector<unsigned long long> off((size_t)n); std::vector<int> cnt((size_t)n);
+  if (n) {
+    CK(cudaMemcpy(key.data(), r_key, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(off.data(), r_off, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt.data(), r_cnt, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(r_key); cudaFree(r_off); cudaFree(r_cnt); cudaFree(r_n);
+  // order: (chunk x, chunk y, chunk z, block x, block y, block z) — equal to chunk order then (lx*bpc+ly)*bpc+lz
+  struct Ord { int c[3]; int b[3]; int idx; };
+  std::vector<Ord> ord((size_t)n);
+  const int bpc = e->P.blocks_per_chunk;
+  for (int i = 0; i < n; i++) {
+    unpack_key(key[i], ord[i].b[0], ord[i].b[1], ord[i].b[2]);
+    for (int a = 0; a < 3; a++) ord[i].c[a] = floor_div(ord[i].b[a], bpc);
+    ord[i].idx = i;
+  }
+  std::sort(ord.begin(), ord.end(), [](const Ord& p, const Ord& q) {
+    for (int a = 0; a < 3; a++) if (p.c[a] != q.c[a]) return p.c[a] < q.c[a];
+    for (int a = 0; a < 3; a++) if (p.b[a] != q.b[a]) return p.b[a] < q.b[a];
+    return false;
+  });
+  mb.key.resize(n); mb.off.resize(n); mb.cnt.resize(n);
+  for (int i = 0; i < n; i++) { mb.key[i] = key[ord[i].idx]; mb.off[i] = off[ord[i].idx]; mb.cnt[i] = cnt[ord[i].idx]; }
+  return VH_OK;
+}
+
+static int extract_mesh_locked(vh_engine* e, int mode, std::vector<vh_triangle>* host_out, vh_triangle* out, uint64_t cap, uint64_t* n_out) {
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  int rc = finish_sync(e);
+  if (rc != VH_OK) return rc;
+  MeshBlocks mb;
+  rc = collect_blocks(e, mode, mb);
+  if (rc != VH_OK) { cudaFree(mb.tmp_arena); return rc; }
+  const int n = (int)mb.key.size();
+  std::vector<unsigned long long> dst((size_t)n);
+  unsigned long long total = 0;
+  for (int i = 0; i < n; i++) { dst[i] = total; total += (unsigned long long)mb.cnt[i]; }
+  if (n_out) *n_out = total;
+  if (host_out) { host_out->resize((size_t)total); out = host_out->data(); cap = total; }
+  if (out && total > 0 && cap >= total) {
+    unsigned long long *d_src = nullptr, *d_dst = nullptr; int* d_cnt = nullptr; vh_triangle* d_out = nullptr;
+    cudaError_t ce = cudaMalloc((void**)&d_src, (size_t)n * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_dst, (size_t)n * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_cnt, (size_t)n * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_out, (size_t)total * sizeof(vh_triangle));
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_src, mb.off.data(), (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_dst, dst.data(), (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_cnt, mb.cnt.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+      launch_gather_triangles(mb.arena, d_src, d_dst, d_cnt, n, d_out, e->stream);
+      ce = cudaStreamSynchronize(e->stream);
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, (size_t)total * sizeof(vh_triangle), cudaMemcpyDeviceToHost);
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_cnt); cudaFree(d_out);
+    if (ce != cudaSuccess) { cudaFree(mb.tmp_arena); return fail(VH_ERR_CUDA, "CUDA Error: %s in vh_extract_mesh", cudaGetErrorString(ce)); }
+  } else if (out && total > cap) {
+    cudaFree(mb.tmp_arena);
+    return fail(VH_ERR_INVALID, "output capacity %llu < %llu triangles", (unsigned long long)cap, total);
+  }
+  cudaFree(mb.tmp_arena);
+  return VH_OK;
+}
+
+int vh_extract_mesh(vh_engine* e, int mode, vh_triangle* out, uint64_t cap, uint64_t* n) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  if (mode != VH_MESH_REF_PERSISTENT && mode != VH_MESH_FULL_MAP) return fail(VH_ERR_INVALID, "unknown mesh mode %d", mode);
+  std::lock_guard<std::mutex> lk(e->mtx);
+  return extract_mesh_locked(e, mode, nullptr, out, cap, n);
+}
+
+// vertex dedupe on exact float xyz, first occurrence's colour wins, coordinates * vox_size (tsdf2mesh, tsdf.cu:1810-1821)
+struct XyzKey { float x, y, z; bool operator==(const XyzKey& o) const { return x == o.x && y == o.y && z == o.z; } };
+struct XyzHash {
+  size_t operator()(const XyzKey& k) const {
+    uint32_t a, b, c; const float x = k.x + 0.0f, y = k.y + 0.0f, z = k.z + 0.0f;   // -0 -> +0 so equal keys hash equally
+    memcpy(&a, &x, 4); memcpy(&b, &y, 4); memcpy(&c, &z, 4);
+    uint64_t h = (uint64_t)a * 0x9E3779B97F4A7C15ull ^ ((uint64_t)b << 21) * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)c * 0x165667B19E3779F9ull;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+
+static void weld(const std::vector<vh_triangle>& tris, float vox_size, std::vector<vh_vertex>& verts, std::vector<int32_t>& faces) {
+  std::unordered_map<XyzKey, int32_t, XyzHash> seen;
+  seen.reserve(tris.size() * 2);
+  faces.resize(tris.size() * 3);
+  for (size_t t = 0; t < tris.size(); t++)
+    for (int j = 0; j < 3; j++) {
+      const vh_vertex& v = tris[t].p[j];
+      auto it = seen.find(XyzKey{v.x, v.y, v.z});
+      if (it == seen.end()) {
+        const int32_t id = (int32_t)verts.size();
+        seen.emplace(XyzKey{v.x, v.y, v.z}, id);
+        vh_vertex s = v; s.x *= vox_size; s.y *= vox_size; s.z *= vox_size; s.pad = 0;
+        verts.push_back(s);
+        faces[3 * t + j] = id;
+      } else faces[3 * t + j] = it->second;
+    }
+}
+
+int vh_weld_mesh(vh_engine* e, int mode, vh_vertex* verts, uint64_t vcap, uint64_t* nv, int32_t* faces, uint64_t fcap, uint64_t* nf) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  std::vector<vh_triangle> tris;
+  int rc = extract_mesh_locked(e, mode, &tris, nullptr, 0, nullptr);
+  if (rc != VH_OK) return rc;
+  std::vector<vh_vertex> v; std::vector<int32_t> f;
+  weld(tris, e->P.vox_size, v, f);
+  if (nv) *nv = v.size();
+  if (nf) *nf = f.size() / 3;
+  if (verts) { if (vcap < v.size()) return fail(VH_ERR_INVALID, "vertex capacity too small"); memcpy(verts, v.data(), v.size() * sizeof(vh_vertex)); }
+  if (faces) { if (fcap < f.size() / 3) return fail(VH_ERR_INVALID, "face capacity too small"); memcpy(faces, f.data(), f.size() * sizeof(int32_t)); }
+  return VH_OK;
+}
+
+int vh_save_ply(vh_engine* e, const char* path, int mode) {
+  if (!e || !path) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  std::vector<vh_triangle> tris;
+  int rc = extract_mesh_locked(e, mode, &tris, nullptr, 0, nullptr);
+  if (rc != VH_OK) return rc;
+  std::vector<vh_vertex> v; std::vector<int32_t> f;
+  weld(tris, e->P.vox_size, v, f);
+  std::ofstream ply(path);
+  if (!ply) return fail(VH_ERR_IO, "cannot open %s", path);
+  // same header and default ostream number formatting as tsdf2mesh (tsdf.cu:1870-1885)
+  ply << "ply\nformat ascii 1.0\ncomment stanford bunny\nelement vertex " << v.size() << "\n";
+  ply << "property float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n";
+  ply << "element face " << f.size() / 3 << "\n";
+  ply << "property list uchar int vertex_index\nend_header\n";
+  for (const auto& p : v) ply << p.x << " " << p.y << " " << p.z << " " << (int)p.r << " " << (int)p.g << " " << (int)p.b << "\n";
+  for (size_t t = 0; t < f.size() / 3; t++) ply << "3 " << f[3 * t] << " " << f[3 * t + 1] << " " << f[3 * t + 2] << "\n";
+  ply.close();
+  if (!ply) return fail(VH_ERR_IO, "write to %s failed", path);
+  return VH_OK;
+}
+
+int vh_host_alloc(void** p, size_t bytes) {
+  if (!p) return fail(VH_ERR_INVALID, "null argument");
+  CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+  return VH_OK;
+}
+int vh_host_free(void* p) { CK(cudaFreeHost(p)); return VH_OK; }
+
+}  // extern "C"

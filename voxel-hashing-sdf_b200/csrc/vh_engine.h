@@ -1,0 +1,89 @@
+// vh_engine.h — internal layout of the engine (host + device views). Not part of the C ABI.
+//
+// HBM layout (all resident for the life of the engine; nothing is streamed to the host on the hot path,
+// unlike the reference's per-frame chunk stream-in/out, /root/reference/src/tsdf.cu:277-457, :469-596):
+//   map.keys   u64 [capacity]        packed block coordinate per entry        8 B/entry
+//   map.slots  i32 [capacity]        pool slot of the entry's block           4 B/entry
+//   stamps     u32 [capacity]        frame number of the last frame that saw the block
+//   sdf        f32 [pool_blocks*512] TSDF plane,   voxel index (x*8+y)*8+z    2 KB/block
+//   wgt        f32 [pool_blocks*512] weight plane                             2 KB/block
+//   rgb        u8x4[pool_blocks*512] colour plane (only when use_color)       2 KB/block
+//   visible    i32 [list_cap]        entry indices of the frame's visible set (compacted)
+//   tri_arena  48 B triangles, bump-allocated per block per frame; tri_offset/tri_count per pool slot
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vh_c.h"
+#include "vh_map.cuh"
+
+namespace vh {
+
+constexpr int VPB = 8;            // voxels per block edge (the reference's VOXEL_PER_BLOCK is 5; BASELINE configs use 8)
+constexpr int BLOCK_VOX = 512;
+
+struct StaticParams {
+  int W, H;
+  float fx, fy, cx, cy;
+  float min_depth, max_depth;
+  float vox_size, trunc, block_size, chunk_size;
+  float half_vox;                 // 0.5f * vox_size (tsdf.cu:2146)
+  int stride, max_steps, bpc;
+  int nrx, nry;                   // sampled rays per row / column (reference launch shape, tsdf.cu:2263-2264)
+  int use_color;
+  uint32_t shard_rank, shard_count;
+};
+
+struct FrameParams {
+  float c2w[16];
+  float fc[3];                    // frustum centre (tsdf.cu:154-161)
+  int cstart[3], cend[3];         // candidate chunk cube (tsdf.cu:304-312)
+  float chunk_test_radius;        // 0.5*CHUNK_RADIUS*sqrt(3)*1.1 (tsdf.cu:172)
+  uint32_t frame;                 // 1-based frame stamp
+};
+
+// per-frame device counters (one 64-byte block, reset by a memset each frame)
+struct FrameCounters {
+  int visible_count;
+  int pad0;
+  unsigned long long voxel_updates;
+  unsigned long long triangles;
+  unsigned long long pad[5];
+};
+
+struct DeviceView {
+  MapView map;
+  uint32_t* stamps;
+  float* sdf;
+  float* wgt;
+  uchar4* rgb;
+  int* visible;
+  int list_cap;
+  FrameCounters* counters;
+  // triangle store
+  vh_triangle* arena;
+  unsigned long long* arena_top;  // triangles used
+  unsigned long long arena_cap;   // triangles
+  unsigned long long* tri_offset; // [pool_blocks]
+  int* tri_count;                 // [pool_blocks]
+  int* engine_error;              // sticky: 1 = arena overflow this frame
+};
+
+// kernels (defined in the .cu files)
+void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st);
+void launch_integrate(const StaticParams& S, const FrameParams& F, const float* d_depth, const uint8_t* d_rgb, const DeviceView& D,
+                      int num_sms, cudaStream_t st);
+void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count,
+                           int full_map, unsigned long long* out_offset, int* out_count, int num_sms, cudaStream_t st);
+void launch_set_visible(const DeviceView& D, const unsigned long long* d_keys, int n, uint32_t frame, cudaStream_t st);
+void launch_list_all_blocks(const DeviceView& D, int* list, int* list_count, cudaStream_t st);
+void launch_gather_blocks(const DeviceView& D, const unsigned long long* d_keys, int n, float* sdf, float* wgt, uint8_t* rgb, uint8_t* found,
+                          cudaStream_t st);
+void launch_checksum(const DeviceView& D, double* d_out4, cudaStream_t st);
+void launch_block_records(const DeviceView& D, const unsigned long long* offsets, const int* counts, unsigned long long* rec_key,
+                          unsigned long long* rec_off, int* rec_cnt, int* n_out, cudaStream_t st);
+void launch_gather_triangles(const vh_triangle* arena, const unsigned long long* src_off, const unsigned long long* dst_off, const int* cnt, int n,
+                             vh_triangle* out, cudaStream_t st);
+void upload_mc_tables();
+
+}  // namespace vh
