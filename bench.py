@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — depth frames/s of the voxel-hashing TSDF hot path (allocate -> integrate -> marching cubes).
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[1], the headline single-GPU config): the synthetic 640x480 sequence of 500 frames at
+5 mm voxels, 8^3 blocks, 2^20-bucket x 4 hash, truncation 2.5 cm, MaxDepth 10, colour images. A *step* is one batch of
+FRAMES_PER_STEP consecutive frames through the whole per-frame path (what the reference's processFrame does:
+upload, visible-block allocation, TSDF integrate, working-set marching cubes); K=10 steps = the 500-frame sequence,
+started from an empty map.
+
+  value   frames/s with the frames already resident in HBM (vh_integrate_device back to back, one sync at the end)
+  e2e     frames/s through the reference-facing call (vh_integrate == GpuTsdfGenerator::processFrame): pinned HOST
+          buffers, the H2D copies of depth+rgb and the D2H read of the frame's counters inside the timed region,
+          synchronous per frame like the reference
+  roofline  the integrate kernel: algorithmic bytes (16 B x voxel updates + 4 W H + 12 B x visible blocks, + colour
+          8 B x updates + 3 W H) / its CUDA-event time, vs the measured HBM copy peak
+  cpu_baseline  the CPU oracle (port of the reference's algorithm, oracle/vh_oracle.c) on this box's host cores,
+          bounded sample of the same workload
+
+N > 1: one process per GPU (torchrun). The path shards by independent maps (BASELINE config 5: one sequence and one
+map per GPU, phase-shifted trajectories), no data-path collective -> "scaling": "weak"; torch.distributed is used
+only for the barrier and the max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_STEP = 50
+METRIC = "depth_frames_per_sec_640x480_5mm"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--no-color", action="store_true")
+    ap.add_argument("--no-mc", action="store_true", help="integration only (F_int); default runs working-set MC every frame like the reference")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, rank):
+    synth = importlib.import_module("voxel-hashing-sdf_b200.synth")
+    cfg = synth.CONFIGS[args.config]
+    # config 5 style for N > 1: every rank gets its own phase-shifted trajectory over the same room
+    sc = synth.make_scene(args.config, color=not args.no_color, phase=0.37 * rank)
+    return synth, cfg, sc
+
+
+def config_dict(args, cfg, sc, world):
+    return {
+        "workload": f"BASELINE config {args.config[1]}: synthetic {sc.width}x{sc.height} depth+rgb sequence, {sc.n_frames} frames, "
+                    f"{cfg['vox_size'] * 1000:g} mm voxels, 8^3 blocks, {cfg['num_buckets']}-bucket x4 hash, trunc {cfg['trunc'] * 100:g} cm, MaxDepth {cfg['max_depth']:g}",
+        "frames_per_step": FRAMES_PER_STEP,
+        "per_frame_path": "upload + allocate + integrate" + ("" if args.no_mc else " + working-set marching cubes"),
+        "color": not args.no_color,
+        "multi_gpu": "one independent sequence+map per GPU (config 5 style), no collective on the data path" if world > 1 else "single map",
+        "l2": "inputs larger than L2: every frame is a distinct 1.2 MB depth (+0.9 MB rgb) image and touches a ~280 MB voxel working set (L2 = 126 MB)",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, frames_wanted, per_step_frames, steps, warmup):
+    """The reference's algorithm on host cores: oracle/vh_oracle.c with all OpenMP threads."""
+    from oracle import binding as ob
+    synth, cfg, sc = workload(args, 0)
+    p = ob.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"], voxels_per_block=8,
+                            use_color=0 if args.no_color else 1, run_mc=0 if args.no_mc else 1, num_threads=0)
+    o = ob.Oracle(p)
+    threads = ob.lib().vo_threads()
+    frames = [sc.frame(i) for i in range(frames_wanted)]
+    i = 0
+    for _ in range(warmup * per_step_frames):
+        o.process_frame(*frames[i % len(frames)]); i += 1
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps * per_step_frames):
+        o.process_frame(*frames[i % len(frames)]); i += 1; n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, dt, threads, n
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    synth, cfg, sc = workload(args, 0)
+    per_step = 1   # bounded sample: one frame of the sequence per step
+    fps, dt, threads, n = cpu_reference_run(args, args.steps + args.warmup, per_step, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, cfg, sc, 1),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} consecutive frames of the workload (1 frame per step, frames {args.warmup}..{args.warmup + n - 1}), "
+                                   f"oracle/vh_oracle.c (CPU restatement of the reference's processFrame, pinned against its emulated tsdf.cu) with OpenMP on {threads} threads"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    vh = importlib.import_module("voxel-hashing-sdf_b200")
+    if not os.path.exists(vh.LIB_PATH):
+        vh.build()
+    synth, cfg, sc = workload(args, rank)
+    color = not args.no_color
+    W, H = sc.width, sc.height
+    n_timed = args.steps * FRAMES_PER_STEP
+    n_warm = args.warmup * FRAMES_PER_STEP
+    n_frames = min(max(n_timed, n_warm), sc.n_frames)
+
+    # ---- synthetic frames: pinned host copies (e2e) and HBM-resident copies (value) ----
+    h_depth = torch.empty((n_frames, H, W), dtype=torch.float32).pin_memory()
+    h_rgb = torch.empty((n_frames, H, W, 3), dtype=torch.uint8).pin_memory()
+    poses = np.zeros((n_frames, 16), np.float32)
+    for i in range(n_frames):
+        d, rgb, c2w = sc.frame(i)
+        h_depth[i] = torch.from_numpy(d); h_rgb[i] = torch.from_numpy(rgb); poses[i] = c2w
+    d_depth = h_depth.cuda(non_blocking=False)
+    d_rgb = h_rgb.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+
+    p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"],
+                            num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=3 << 20,
+                            use_color=1 if color else 0, mc_per_frame=0 if args.no_mc else 1, device=local, tri_arena_bytes=8 << 30)
+    eng = vh.TsdfEngine(p)
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    dptr = lambda t, i: t[i].data_ptr()
+    rgb_dev = (lambda i: dptr(d_rgb, i)) if color else (lambda i: None)
+    rgb_host = (lambda i: dptr(h_rgb, i)) if color else (lambda i: None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def frames_of(n):
+        return [i % n_frames for i in range(n)]
+
+    # ---- warm-up (untimed), then start the timed sequences from an empty map ----
+    for i in frames_of(n_warm):
+        eng.integrate_device(dptr(d_depth, i), rgb_dev(i), poses[i])
+    eng.sync()
+    for i in frames_of(min(n_warm, 2 * FRAMES_PER_STEP)):
+        eng.processFrame(h_depth[i].numpy(), h_rgb[i].numpy() if color else None, poses[i])
+
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # ---- value: inputs resident in HBM ----
+    eng.reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in frames_of(n_timed):
+        eng.integrate_device(dptr(d_depth, i), rgb_dev(i), poses[i])
+    e1.record(stream)
+    eng.sync()
+    barrier()
+    ms_value = max_over_ranks(e0.elapsed_time(e1))
+    st_end = eng.stats()
+
+    # ---- e2e: the reference-facing synchronous call with pinned host buffers ----
+    eng.reset()
+    barrier()
+    L = eng.L
+    hp = eng.h
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in frames_of(n_timed):
+        rc = L.vh_integrate(hp, dptr(h_depth, i), rgb_host(i), poses[i].ctypes.data)
+        if rc != 0:
+            raise vh.VhError(rc, L.vh_last_error().decode())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall_e2e = (time.perf_counter() - t0) * 1000.0
+    barrier()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_e2e))
+
+    # ---- per-kernel profile pass (untimed for the headline): CUDA-event time of every stage of every frame ----
+    eng.reset()
+    acc = dict(alloc=0.0, integrate=0.0, mc=0.0, upload=0.0, updates=0, visible=0, tris=0)
+    for i in frames_of(n_timed):
+        eng.integrate_device(dptr(d_depth, i), rgb_dev(i), poses[i])
+        s = eng.stats()
+        acc["alloc"] += s.ms_alloc; acc["integrate"] += s.ms_integrate; acc["mc"] += s.ms_mc
+        acc["updates"] += s.voxel_updates; acc["visible"] += s.visible_blocks; acc["tris"] += s.triangles
+    clocks = sampler.stop() if sampler else None
+    allocated = eng.stats().allocated_blocks
+
+    total_frames = sum_over_ranks(float(n_timed))
+    value = total_frames / (ms_value / 1000.0)
+    e2e = total_frames / (ms_e2e / 1000.0)
+    upd_per_frame = acc["updates"] / n_timed
+    vis_per_frame = acc["visible"] / n_timed
+    tris_per_frame = acc["tris"] / n_timed
+    bytes_int = 16.0 * upd_per_frame + 4.0 * W * H + 12.0 * vis_per_frame + ((8.0 * upd_per_frame + 3.0 * W * H) if color else 0.0)
+    bytes_mc = (4.0 + (3.0 if color else 0.0)) * 512 * vis_per_frame + 48.0 * tris_per_frame + 12.0 * vis_per_frame
+    ms_int = acc["integrate"] / n_timed
+    ms_mc = acc["mc"] / n_timed
+    ms_alloc = acc["alloc"] / n_timed
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    ach = bytes_int / (ms_int * 1e-3) / 1e9 if ms_int > 0 else 0.0
+
+    h2d = W * H * 4 + (W * H * 3 if color else 0) + 64
+    d2h = 104
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, cfg, sc, world),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * FRAMES_PER_STEP, "d2h_bytes_per_step": d2h * FRAMES_PER_STEP,
+                "call": "vh_integrate (GpuTsdfGenerator::processFrame drop-in), pinned host depth+rgb, synchronous per frame"},
+        "gpu_launches": 3 * n_timed if not args.no_mc else 2 * n_timed,
+        "voxel_updates_per_sec": sum_over_ranks(float(acc["updates"])) / (ms_value / 1000.0),
+        "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "triangles": tris_per_frame,
+                      "ms_alloc": ms_alloc, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated},
+        "roofline": {"kernel": "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int},
+        "roofline_mc": {"kernel": "vh::marching_cubes_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
+                        "peak": peak, "unit": "GB/s", "algorithmic_bytes_per_launch": bytes_mc, "avg_launch_ms": ms_mc},
+        "clocks": clocks,
+    }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            fps, dt, threads, n = cpu_reference_run(args, args.cpu_frames, 1, args.cpu_frames, 0)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {n} frames of the same workload ({dt:.1f} s), oracle/vh_oracle.c with OpenMP on {threads} threads"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

@@ -224,7 +224,7 @@ def test_full_size_properties_5mm(vh, synth):
             seen |= key_set(vis)
         assert key_set(a.allocated_keys()) == seen                               # allocated == union of visible sets
         ca, cb = a.checksum(), b.checksum()
-        assert ca == cb                                                          # deterministic across engines
+        assert all(ca[k] == cb[k] for k in ("sum_w", "n_observed", "n_negative")) and abs(ca["sum_sdf"] - cb["sum_sdf"]) <= 1e-9 * abs(ca["sum_sdf"])   # deterministic map (double sums are order-dependent)
         assert ca["sum_w"] == total_updates                                      # every update adds exactly 1 to one weight
         keys = sort_keys(a.allocated_keys())[:2000]
         sdf, w, _, _ = a.download_blocks(keys, want_rgb=False)
