@@ -79,6 +79,7 @@ typedef struct vh_stats {
   uint64_t triangles;           /* valid triangles emitted for the last frame's working set */
   uint64_t arena_triangles;     /* triangles currently held in the arena (live + superseded) */
   float ms_upload, ms_alloc, ms_integrate, ms_mc;   /* CUDA-event times of the last frame's stages */
+  uint64_t debug_mismatches;    /* with env VH_INTEGRATE_VERIFY=1: fast-path vs IEEE-path disagreements in the last frame (must be 0) */
 } vh_stats;
 
 /* vertex layout of the triangle soup: the reference's Vertex (tsdf.cuh:65-77), 16 bytes */

@@ -238,3 +238,21 @@ def test_full_size_properties_5mm(vh, synth):
         a.processFrame(d, None, c2w)
         assert a.stats().voxel_updates == before
         assert a.checksum()["sum_w"] == total_updates + before
+
+
+def test_fast_projection_and_divisions_agree_with_ieee_path(vh, synth, monkeypatch):
+    """VH_INTEGRATE_VERIFY=1 makes the integrate kernel evaluate, for every voxel, both its fast path (approximate
+    projection + tie guard, shared-reciprocal divisions) and the plain IEEE expressions of the reference, counting any
+    disagreement in pixel choice, dist, sdf or colour. Over full-size frames the count must be exactly zero."""
+    monkeypatch.setenv("VH_INTEGRATE_VERIFY", "1")
+    for name, kw in (("C2", dict(vox_size=0.005, trunc_margin=0.025)), ("C1", dict(vox_size=0.01, trunc_margin=0.05))):
+        sc = synth.make_scene(name, color=True, holes=0.01)
+        p = vh.params_for_scene(sc, max_depth=10.0, use_color=1, num_buckets=1 << 20, pool_blocks=1 << 20, mc_per_frame=0, **kw)
+        with vh.TsdfEngine(p) as eng:
+            total = 0
+            for i in list(range(0, 12)) + [0, 1, 2, 3]:          # revisits: weights > 1 exercise the shared-reciprocal divisions
+                eng.processFrame(*sc.frame(i))
+                st = eng.stats()
+                assert st.debug_mismatches == 0, f"{name} frame {i}: {st.debug_mismatches} fast/IEEE disagreements"
+                total += st.voxel_updates
+            assert total > 5e7

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <mutex>
@@ -204,6 +205,9 @@ int vh_create(const vh_params* p, vh_engine** out) {
   S.nry = std::min(gy, (p->height + p->dda_stride - 1) / p->dda_stride);
   S.use_color = p->use_color ? 1 : 0;
   S.shard_rank = (uint32_t)p->shard_rank; S.shard_count = (uint32_t)p->shard_count;
+  // approximate-projection error is < 7e-7 * |pixel coordinate| (vh_integrate.cu); 2e-3 px covers images up to ~2000 px
+  S.round_eps = std::max(2e-3f, 1e-3f + 1e-6f * (float)std::max(p->width, p->height));
+  { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
 
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket;
   uint64_t cap = 1024;
@@ -570,6 +574,7 @@ int vh_get_stats(vh_engine* e, vh_stats* out) {
   out->voxel_updates_total = 0;
   out->triangles = e->h_block->c.triangles;
   out->arena_triangles = e->h_block->arena_top;
+  out->debug_mismatches = e->h_block->c.pad[0];
   if (e->frames > 0) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) out->ms_upload = ms;

@@ -32,6 +32,8 @@ struct StaticParams {
   int nrx, nry;                   // sampled rays per row / column (reference launch shape, tsdf.cu:2263-2264)
   int use_color;
   uint32_t shard_rank, shard_count;
+  float round_eps;                // distance from a .5 pixel tie below which integrate re-projects with IEEE divisions
+  int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
 };
 
 struct FrameParams {

@@ -20,8 +20,6 @@
 
 namespace vh {
 
-constexpr int MC_THREADS = 512;
-constexpr int TILE = 9, TILE_N = TILE * TILE * TILE;
 
 // corner numbering of the reference's idxMap (tsdf.cuh:234-241) and Bourke's edge -> corner pairs, as arithmetic
 // (same values as VH_MC_CORNER_OFFSET / VH_MC_EDGE_CORNERS in include/vh_mc_tables.h, usable in device code)
@@ -76,151 +74,198 @@ __device__ __forceinline__ Vtx vertex_interp(const Vtx& p1, const Vtx& p2, float
 
 __device__ __forceinline__ bool same_pos(const Vtx& a, const Vtx& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
+constexpr int MC_WARPS = 8;                 // voxel blocks in flight per CTA (one warp each)
+constexpr int MC_THREADS = MC_WARPS * 32;
+constexpr int TILE = 9, TILE_N = TILE * TILE * TILE, TILE_PAD = 736;
+
+struct McBlock {            // per-warp context of the block being meshed
+  const float* tile;        // 9^3 sdf tile in shared memory
+  const int* nb_slot;       // pool slots of the 8 corner blocks (bit0 +x, bit1 +y, bit2 +z), -1 = absent
+  int bx, by, bz;
+};
+
+// vertex on cube edge e of the voxel at tile position (lx,ly,lz)
+__device__ __forceinline__ Vtx edge_vertex(const McBlock& B, const DeviceView& D, int lx, int ly, int lz, int e, bool color) {
+  const int a = e < 8 ? e : e - 8;
+  const int b = e < 4 ? ((e + 1) & 3) : (e < 8 ? 4 + ((e - 3) & 3) : e - 4);
+  const int ax = lx + corner_ox(a), ay = ly + corner_oy(a), az = lz + corner_oz(a);
+  const int qx = lx + corner_ox(b), qy = ly + corner_oy(b), qz = lz + corner_oz(b);
+  Vtx pa, pb;
+  pa.x = i2f(B.bx * VPB + ax); pa.y = i2f(B.by * VPB + ay); pa.z = i2f(B.bz * VPB + az);      // Vertex(cxi, cyi, czi), tsdf.cu:931
+  pb.x = i2f(B.bx * VPB + qx); pb.y = i2f(B.by * VPB + qy); pb.z = i2f(B.bz * VPB + qz);
+  pa.c = 0; pb.c = 0;
+  if (color) {
+    const int sa = B.nb_slot[(ax >> 3) | ((ay >> 3) << 1) | ((az >> 3) << 2)], sb = B.nb_slot[(qx >> 3) | ((qy >> 3) << 1) | ((qz >> 3) << 2)];
+    const uchar4 ca = D.rgb[(size_t)sa * BLOCK_VOX + ((ax & 7) * 64 + (ay & 7) * 8 + (az & 7))];
+    const uchar4 cb = D.rgb[(size_t)sb * BLOCK_VOX + ((qx & 7) * 64 + (qy & 7) * 8 + (qz & 7))];
+    pa.c = (uint32_t)ca.x | ((uint32_t)ca.y << 8) | ((uint32_t)ca.z << 16);
+    pb.c = (uint32_t)cb.x | ((uint32_t)cb.y << 8) | ((uint32_t)cb.z << 16);
+  }
+  return vertex_interp(pa, pb, B.tile[(ax * TILE + ay) * TILE + az], B.tile[(qx * TILE + qy) * TILE + qz], color);
+}
+
+__device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int lz) {
+  int cube = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    cube |= (tile[((lx + corner_ox(k)) * TILE + (ly + corner_oy(k))) * TILE + (lz + corner_oz(k))] < 0.0f) ? (1 << k) : 0;   // tsdf.cu:978-986, no weight test (Q4)
+  return cube;
+}
+
+// One warp per voxel block, persistent over the list. Pass 1 finds which triangles survive, pass 2 writes them.
 __global__ void __launch_bounds__(MC_THREADS)
 marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int* __restrict__ list,
                       const int* __restrict__ list_count, const int full_map, unsigned long long* __restrict__ out_offset,
                       int* __restrict__ out_count) {
-  __shared__ float s_sdf[TILE_N];
-  __shared__ uint32_t s_rgb[TILE_N];
-  __shared__ int s_nb_slot[8];
-  __shared__ int s_warp_sum[MC_THREADS / 32];
-  __shared__ unsigned long long s_base;
-  __shared__ int s_total;
+  __shared__ float s_tile[MC_WARPS][TILE_PAD];
+  __shared__ int s_nb[MC_WARPS][8];
+  __shared__ signed char s_tri[256 * 16];
+  __shared__ unsigned char s_ntri[256];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < 256 * 16; i += MC_THREADS) s_tri[i] = c_tri[i >> 4][i & 15];
+  for (int i = tid; i < 256; i += MC_THREADS) s_ntri[i] = c_ntri[i];
+  __syncthreads();
+
   const int n = min(*list_count, D.list_cap);
   const bool color = S.use_color != 0;
+  const int gwarp = blockIdx.x * MC_WARPS + wid, nwarps = gridDim.x * MC_WARPS;
+  float* tile = s_tile[wid];
   unsigned long long my_tris = 0;
 
-  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+  for (int i = gwarp; i < n; i += nwarps) {
     const int entry = list[i];
     const u64 key = D.map.keys[entry];
     const int slot = D.map.slots[entry];
-    int bx, by, bz;
-    unpack_key(key, bx, by, bz);
+    McBlock B;
+    unpack_key(key, B.bx, B.by, B.bz);
+    B.tile = tile; B.nb_slot = s_nb[wid];
 
-    // 1. the block and its seven +x/+y/+z neighbours; bit0 = +x, bit1 = +y, bit2 = +z
-    if (tid < 8) {
-      int s = -1;
-      if (tid == 0) s = slot;
-      else {
-        const int nx = bx + (tid & 1), ny = by + ((tid >> 1) & 1), nz = bz + ((tid >> 2) & 1);
-        if (key_in_range(nx, ny, nz)) {
-          const int e = map_find(D.map, pack_key(nx, ny, nz));
-          if (e >= 0 && (full_map || D.stamps[e] == frame)) s = D.map.slots[e];
+    // the block and its seven +x/+y/+z neighbours: one lock-free probe per lane; a neighbour counts only if it is in the
+    // same list (this frame's working set, tsdf.cu:930,957-969) or, for full-map extraction, allocated at all
+    int nb = -1;
+    if (lane == 0) nb = slot;
+    else if (lane < 8) {
+      const int nx = B.bx + (lane & 1), ny = B.by + ((lane >> 1) & 1), nz = B.bz + ((lane >> 2) & 1);
+      if (key_in_range(nx, ny, nz)) {
+        const int e = map_find(D.map, pack_key(nx, ny, nz));
+        if (e >= 0 && (full_map || D.stamps[e] == frame)) nb = D.map.slots[e];
+      }
+    }
+    const unsigned present = __ballot_sync(0xffffffffu, nb >= 0) & 0xFFu;
+    if (lane < 8) s_nb[wid][lane] = nb;
+    __syncwarp();
+    // okbits bit q: every corner block a voxel with boundary mask q touches is present
+    bool okq = false;
+    if (lane < 8) {
+      okq = true;
+#pragma unroll
+      for (int m = 0; m < 8; m++) if ((m & lane) == m && !((present >> m) & 1u)) okq = false;
+    }
+    const unsigned okbits = __ballot_sync(0xffffffffu, okq) & 0xFFu;
+
+    // 9^3 tile: own 8^3 as four float4 per lane, then the 217 halo cells
+    if (slot >= 0) {
+      const float* src = D.sdf + (size_t)slot * BLOCK_VOX;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int v = (j * 32 + lane) * 4;
+        const float4 q = *reinterpret_cast<const float4*>(src + v);
+        float* dst = tile + ((v >> 6) * TILE + ((v >> 3) & 7)) * TILE + (v & 7);
+        dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+      }
+    }
+    for (int c = lane; c < 217; c += 32) {
+      int tx, ty, tz;
+      if (c < 81) { tx = 8; ty = c / 9; tz = c - ty * 9; }
+      else if (c < 153) { const int q = c - 81; tx = q / 9; ty = 8; tz = q - tx * 9; }
+      else { const int q = c - 153; tx = q >> 3; ty = q & 7; tz = 8; }
+      const int m = (tx >> 3) | ((ty >> 3) << 1) | ((tz >> 3) << 2);
+      const int s = s_nb[wid][m];
+      tile[(tx * TILE + ty) * TILE + tz] = s >= 0 ? D.sdf[(size_t)s * BLOCK_VOX + ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))] : 0.0f;
+    }
+    __syncwarp();
+
+    // pass 1: which triangles survive. Reference thread -> voxel mapping (tsdf.cu:903-906) for VPB = 8:
+    // tid = j*32 + lane  ->  x = tid >> 6, y = ((tid >> 3) - bz) & 7, z = tid & 7
+    unsigned long long vlo = 0;   // valid bits of j = 0..11 (5 per j)
+    unsigned vhi = 0;             // j = 12..15
+    int cnt = 0;
+    if (slot >= 0) {
+#pragma unroll 1
+      for (int j = 0; j < 16; j++) {
+        const int t = j * 32 + lane;
+        const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
+        const int need = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);
+        int cube = 0;
+        if ((okbits >> need) & 1u) cube = cube_index(tile, lx, ly, lz);
+        const bool surf = cube != 0 && cube != 255;
+        if (!__any_sync(0xffffffffu, surf)) continue;
+        unsigned valid = 0;
+        if (surf) {
+          const int ntri = s_ntri[cube];
+          for (int k = 0; k < ntri; k++) {
+            const Vtx p0 = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k], false);
+            const Vtx p1 = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k + 1], false);
+            const Vtx p2 = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k + 2], false);
+            if (!(same_pos(p0, p1) || same_pos(p1, p2))) valid |= 1u << k;     // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
+          }
         }
-      }
-      s_nb_slot[tid] = s;
-    }
-    __syncthreads();
-
-    // 2. 9^3 tile
-    for (int c = tid; c < TILE_N; c += MC_THREADS) {
-      const int tx = c / (TILE * TILE), ty = (c / TILE) % TILE, tz = c % TILE;
-      const int nb = (tx == 8 ? 1 : 0) | (ty == 8 ? 2 : 0) | (tz == 8 ? 4 : 0);
-      const int s = s_nb_slot[nb];
-      float v = 0.0f;
-      uint32_t col = 0;
-      if (s >= 0) {
-        const size_t a = (size_t)s * BLOCK_VOX + ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7));
-        v = D.sdf[a];
-        if (color) { const uchar4 q = D.rgb[a]; col = (uint32_t)q.x | ((uint32_t)q.y << 8) | ((uint32_t)q.z << 16); }
-      }
-      s_sdf[c] = v;
-      s_rgb[c] = col;
-    }
-    __syncthreads();
-
-    // 3. pass 1: per-voxel triangles. Reference thread mapping (tsdf.cu:903-906) for VPB = 8.
-    const int lx = tid >> 6, ly = ((tid >> 3) - bz) & 7, lz = tid & 7;
-    const int need = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);
-    bool have = slot >= 0;
-#pragma unroll
-    for (int m = 1; m < 8; m++)
-      if ((m & need) == m && s_nb_slot[m] < 0) have = false;     // a cube corner lies in a block that is not in the list
-
-    int cube = 0;
-    float val[8];
-    if (have) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        val[k] = s_sdf[((lx + corner_ox(k)) * TILE + (ly + corner_oy(k))) * TILE + (lz + corner_oz(k))];
-        cube |= (val[k] < 0.0f) ? (1 << k) : 0;                    // tsdf.cu:978-986 (no weight test, Q4)
+        if (j < 12) vlo |= (unsigned long long)valid << (5 * j); else vhi |= valid << (5 * (j - 12));
+        cnt += __popc(valid);
       }
     }
-    const int ntri = have ? c_ntri[cube] : 0;
-    unsigned valid = 0;      // bit k: triangle k survives the degenerate rule
-    Vtx tv[5][3];
-    if (ntri) {
-      const unsigned em = c_edge_mask[cube];
-      Vtx vl[12];
+    int total = cnt;
 #pragma unroll
-      for (int e = 0; e < 12; e++) {
-        if (em & (1u << e)) {
-          const int a = edge_a(e), b = edge_b(e);
-          Vtx pa, pb;
-          const int ax = lx + corner_ox(a), ay = ly + corner_oy(a), az = lz + corner_oz(a);
-          const int qx = lx + corner_ox(b), qy = ly + corner_oy(b), qz = lz + corner_oz(b);
-          pa.x = i2f(bx * VPB + ax); pa.y = i2f(by * VPB + ay); pa.z = i2f(bz * VPB + az);          // Vertex(cxi, cyi, czi), tsdf.cu:931
-          pb.x = i2f(bx * VPB + qx); pb.y = i2f(by * VPB + qy); pb.z = i2f(bz * VPB + qz);
-          pa.c = s_rgb[(ax * TILE + ay) * TILE + az];
-          pb.c = s_rgb[(qx * TILE + qy) * TILE + qz];
-          vl[e] = vertex_interp(pa, pb, val[a], val[b], color);
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+
+    unsigned long long base = 0;
+    bool fits = true;
+    if (total > 0) {
+      if (lane == 0) {
+        base = atomicAdd(D.arena_top, (unsigned long long)total);
+        if (base + (unsigned long long)total > D.arena_cap) { atomicOr(D.engine_error, 1); fits = false; }
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      fits = __shfl_sync(0xffffffffu, fits, 0);
+    }
+    if (lane == 0 && slot >= 0) { out_offset[slot] = base; out_count[slot] = (total > 0 && fits) ? total : 0; }
+
+    // pass 2: emit in the reference's slot order (tid ascending, k ascending)
+    if (total > 0 && fits) {
+      int running = 0;
+#pragma unroll 1
+      for (int j = 0; j < 16; j++) {
+        const unsigned valid = j < 12 ? (unsigned)((vlo >> (5 * j)) & 31ull) : ((vhi >> (5 * (j - 12))) & 31u);
+        const int c = __popc(valid);
+        if (!__any_sync(0xffffffffu, c > 0)) continue;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (c) {
+          const int t = j * 32 + lane;
+          const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
+          const int cube = cube_index(tile, lx, ly, lz);
+          unsigned long long pos = base + (unsigned long long)(running + incl - c);
+          for (int k = 0; k < 5; k++) {
+            if (valid & (1u << k)) {
+              uint4* dst = reinterpret_cast<uint4*>(D.arena + pos);
+#pragma unroll
+              for (int m = 0; m < 3; m++) {
+                const Vtx p = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k + m], color);
+                dst[m] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), p.c);
+              }
+              ++pos;
+            }
+          }
         }
+        running += __shfl_sync(0xffffffffu, incl, 31);
       }
-      for (int k = 0; k < ntri; k++) {
-        const Vtx p0 = vl[c_tri[cube][3 * k]], p1 = vl[c_tri[cube][3 * k + 1]], p2 = vl[c_tri[cube][3 * k + 2]];
-        tv[k][0] = p0; tv[k][1] = p1; tv[k][2] = p2;
-        if (!(same_pos(p0, p1) || same_pos(p1, p2))) valid |= 1u << k;   // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
-      }
+      if (lane == 0) my_tris += (unsigned long long)total;
     }
-    const int cnt = __popc(valid);
-
-    // CTA exclusive scan of cnt in tid order
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) s_warp_sum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      int w = lane < MC_THREADS / 32 ? s_warp_sum[lane] : 0;
-#pragma unroll
-      for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-      if (lane < MC_THREADS / 32) s_warp_sum[lane] = w;   // inclusive over warps
-      if (lane == MC_THREADS / 32 - 1) {
-        s_total = w;
-        unsigned long long base = 0;
-        if (w > 0) {
-          base = atomicAdd(D.arena_top, (unsigned long long)w);
-          if (base + (unsigned long long)w > D.arena_cap) { atomicOr(D.engine_error, 1); s_total = -w; }
-        }
-        s_base = base;
-      }
-    }
-    __syncthreads();
-    const int total = s_total;
-    const unsigned long long base = s_base;
-    if (tid == 0 && slot >= 0) {
-      out_offset[slot] = base;
-      out_count[slot] = total > 0 ? total : 0;
-    }
-    // 4. pass 2: emit
-    if (cnt && total > 0) {
-      unsigned long long pos = base + (unsigned long long)((wid ? s_warp_sum[wid - 1] : 0) + incl - cnt);
-      for (int k = 0; k < ntri; k++) {
-        if (valid & (1u << k)) {
-          uint4* dst = reinterpret_cast<uint4*>(D.arena + pos);
-#pragma unroll
-          for (int j = 0; j < 3; j++)
-            dst[j] = make_uint4(__float_as_uint(tv[k][j].x), __float_as_uint(tv[k][j].y), __float_as_uint(tv[k][j].z), tv[k][j].c);
-          ++pos;
-        }
-      }
-    }
-    if (tid == 0 && total > 0) my_tris += (unsigned long long)total;
-    __syncthreads();   // smem reuse by the next block
+    __syncwarp();   // the tile is reused by the next block
   }
-  if (tid == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
+  if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
 
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count, int full_map,
