@@ -49,6 +49,8 @@ struct vh_engine {
   cudaStream_t stream = nullptr, upload = nullptr;
   float* d_depth[2] = {nullptr, nullptr};
   uint8_t* d_rgb[2] = {nullptr, nullptr};
+  uint2* d_px[2] = {nullptr, nullptr};     // packed {depth, rgb} records the integrate kernel reads
+  int px_ring = 0;
   cudaEvent_t ev_uploaded[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   bool buf_used[2] = {false, false};
   int ring = 0;
@@ -132,7 +134,7 @@ static int free_engine(vh_engine* e) {
   cudaFree(D.counters); cudaFree(D.arena); cudaFree(D.arena_top); cudaFree(D.tri_offset); cudaFree(D.tri_count); cudaFree(e->d_flags);
   cudaFree(e->d_full_list); cudaFree(e->d_full_count); cudaFree(e->d_full_off); cudaFree(e->d_full_cnt); cudaFree(e->d_keys_tmp);
   for (int i = 0; i < 2; i++) {
-    cudaFree(e->d_depth[i]); cudaFree(e->d_rgb[i]);
+    cudaFree(e->d_depth[i]); cudaFree(e->d_rgb[i]); cudaFree(e->d_px[i]);
     if (e->ev_uploaded[i]) cudaEventDestroy(e->ev_uploaded[i]);
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
   }
@@ -248,6 +250,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   for (int i = 0; i < 2; i++) {
     ALLOC(e->d_depth[i], npx * sizeof(float));
     ALLOC(e->d_rgb[i], npx * 3);
+    ALLOC(e->d_px[i], npx * sizeof(uint2));
   }
 #undef ALLOC
   D.map.mask = e->capacity - 1;
@@ -333,8 +336,10 @@ static int enqueue_stages(vh_engine* e, bool do_alloc) {
     CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
     launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
   }
+  uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
+  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, e->stream);
   CK(cudaEventRecord(e->ev[2], e->stream));
-  launch_integrate(e->S, e->F, e->cur_depth, e->cur_rgb, D, e->num_sms, e->stream);
+  launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->P.mc_per_frame)
     launch_marching_cubes(e->S, e->F, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, e->num_sms, e->stream);
@@ -503,7 +508,9 @@ int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb)
   const int keep = e->S.use_color;
   e->S.use_color = e->cur_rgb ? keep : 0;
   CK(cudaMemsetAsync(&e->D.counters->voxel_updates, 0, sizeof(unsigned long long), e->stream));
-  launch_integrate(e->S, e->F, e->cur_depth, e->cur_rgb, e->D, e->num_sms, e->stream);
+  uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
+  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, e->stream);
+  launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, e->D, e->num_sms, e->stream);
   e->S.use_color = keep;
   int rc = enqueue_readback(e);
   if (rc != VH_OK) return rc;

@@ -73,8 +73,9 @@ struct DeviceView {
 
 // kernels (defined in the .cu files)
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st);
-void launch_integrate(const StaticParams& S, const FrameParams& F, const float* d_depth, const uint8_t* d_rgb, const DeviceView& D,
-                      int num_sms, cudaStream_t st);
+void launch_pack_frame(const float* d_depth, const uint8_t* d_rgb, uint2* d_out, int npx, cudaStream_t st);
+void launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* d_frame_px, bool color, const DeviceView& D, int num_sms,
+                      cudaStream_t st);
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count,
                            int full_map, unsigned long long* out_offset, int* out_count, int num_sms, cudaStream_t st);
 void launch_set_visible(const DeviceView& D, const unsigned long long* d_keys, int n, uint32_t frame, cudaStream_t st);

@@ -133,6 +133,19 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
   float* tile = s_tile[wid];
   unsigned long long my_tris = 0;
 
+  // halo cells handled by this lane, the same for every block: tile offset << 12 | corner-block index << 9 | voxel in that block
+  int halo[7];
+#pragma unroll
+  for (int h = 0; h < 7; h++) {
+    const int c = h * 32 + lane;
+    int tx, ty, tz;
+    if (c < 81) { tx = 8; ty = c / 9; tz = c - ty * 9; }
+    else if (c < 153) { const int q = c - 81; tx = q / 9; ty = 8; tz = q - tx * 9; }
+    else { const int q = c - 153; tx = q >> 3; ty = q & 7; tz = 8; }
+    const int m = (tx >> 3) | ((ty >> 3) << 1) | ((tz >> 3) << 2);
+    halo[h] = c < 217 ? ((((tx * TILE + ty) * TILE + tz) << 12) | (m << 9) | ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))) : -1;
+  }
+
   for (int i = gwarp; i < n; i += nwarps) {
     const int entry = list[i];
     const u64 key = D.map.keys[entry];
@@ -164,7 +177,9 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
     }
     const unsigned okbits = __ballot_sync(0xffffffffu, okq) & 0xFFu;
 
-    // 9^3 tile: own 8^3 as four float4 per lane, then the 217 halo cells
+    // 9^3 tile: own 8^3 as four float4 per lane, then the 217 halo cells. While loading, note whether any cell is
+    // negative / non-negative: a tile of one sign class has cube index 0 or 255 everywhere and yields no triangle.
+    bool any_neg = false, any_pos = false;
     if (slot >= 0) {
       const float* src = D.sdf + (size_t)slot * BLOCK_VOX;
 #pragma unroll
@@ -173,16 +188,25 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
         const float4 q = *reinterpret_cast<const float4*>(src + v);
         float* dst = tile + ((v >> 6) * TILE + ((v >> 3) & 7)) * TILE + (v & 7);
         dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+        any_neg = any_neg || q.x < 0.0f || q.y < 0.0f || q.z < 0.0f || q.w < 0.0f;
+        any_pos = any_pos || !(q.x < 0.0f) || !(q.y < 0.0f) || !(q.z < 0.0f) || !(q.w < 0.0f);
       }
     }
-    for (int c = lane; c < 217; c += 32) {
-      int tx, ty, tz;
-      if (c < 81) { tx = 8; ty = c / 9; tz = c - ty * 9; }
-      else if (c < 153) { const int q = c - 81; tx = q / 9; ty = 8; tz = q - tx * 9; }
-      else { const int q = c - 153; tx = q >> 3; ty = q & 7; tz = 8; }
-      const int m = (tx >> 3) | ((ty >> 3) << 1) | ((tz >> 3) << 2);
-      const int s = s_nb[wid][m];
-      tile[(tx * TILE + ty) * TILE + tz] = s >= 0 ? D.sdf[(size_t)s * BLOCK_VOX + ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))] : 0.0f;
+#pragma unroll
+    for (int h = 0; h < 7; h++) {
+      const int d = halo[h];
+      if (d >= 0) {
+        const int s = s_nb[wid][(d >> 9) & 7];
+        const float v = s >= 0 ? D.sdf[(size_t)s * BLOCK_VOX + (d & 511)] : 0.0f;
+        tile[d >> 12] = v;
+        any_neg = any_neg || v < 0.0f;
+        any_pos = any_pos || !(v < 0.0f);
+      }
+    }
+    const bool mixed = __any_sync(0xffffffffu, any_neg) && __any_sync(0xffffffffu, any_pos);
+    if (!mixed || slot < 0) {
+      if (lane == 0 && slot >= 0) { out_offset[slot] = 0; out_count[slot] = 0; }
+      continue;
     }
     __syncwarp();
 
