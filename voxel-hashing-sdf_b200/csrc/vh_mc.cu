@@ -50,11 +50,13 @@ void upload_mc_tables() {
 struct Vtx { float x, y, z; uint32_t c; };   // c = r | g<<8 | b<<16
 
 // VertexInterp with isolevel 0 (tsdf.cu:1640-1660). The reference compares float fabs() results against the
-// double literal 0.00001; the comparisons are done in double here for the same outcome.
+// double literal 0.00001; the equivalent float threshold is used here.
 __device__ __forceinline__ Vtx vertex_interp(const Vtx& p1, const Vtx& p2, float v1, float v2, bool color) {
-  if ((double)fabsf(fsub(0.0f, v1)) < 0.00001) return p1;
-  if ((double)fabsf(fsub(0.0f, v2)) < 0.00001) return p2;
-  if ((double)fabsf(fsub(v1, v2)) < 0.00001) return p1;
+  // (double)|x| < 0.00001  <=>  |x| <= 0x3727C5AC (the largest float below the double 1e-5; its successor is above it)
+  const float eps = __uint_as_float(0x3727C5ACu);
+  if (fabsf(fsub(0.0f, v1)) <= eps) return p1;
+  if (fabsf(fsub(0.0f, v2)) <= eps) return p2;
+  if (fabsf(fsub(v1, v2)) <= eps) return p1;
   const float mu = fdiv(fsub(0.0f, v1), fsub(v2, v1));
   Vtx p;
   p.x = fadd(p1.x, fmul(mu, fsub(p2.x, p1.x)));
@@ -74,9 +76,9 @@ __device__ __forceinline__ Vtx vertex_interp(const Vtx& p1, const Vtx& p2, float
 
 __device__ __forceinline__ bool same_pos(const Vtx& a, const Vtx& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
-constexpr int MC_WARPS = 8;                 // voxel blocks in flight per CTA (one warp each)
+constexpr int MC_WARPS = 4;                 // voxel blocks in flight per CTA (one warp each); 36.7 KB of static shared memory
 constexpr int MC_THREADS = MC_WARPS * 32;
-constexpr int TILE = 9, TILE_N = TILE * TILE * TILE, TILE_PAD = 736;
+constexpr int TILE = 9, TILE_PAD = 736;   // 9^3 = 729 cells, padded
 
 struct McBlock {            // per-warp context of the block being meshed
   const float* tile;        // 9^3 sdf tile in shared memory
@@ -119,6 +121,7 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
                       int* __restrict__ out_count) {
   __shared__ float s_tile[MC_WARPS][TILE_PAD];
   __shared__ int s_nb[MC_WARPS][8];
+  __shared__ unsigned short s_list[MC_WARPS][BLOCK_VOX * 5];   // candidate triangles of the block in flight
   __shared__ signed char s_tri[256 * 16];
   __shared__ unsigned char s_ntri[256];
 
@@ -210,91 +213,75 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
     }
     __syncwarp();
 
-    // pass 1: which triangles survive. Reference thread -> voxel mapping (tsdf.cu:903-906) for VPB = 8:
-    // tid = j*32 + lane  ->  x = tid >> 6, y = ((tid >> 3) - bz) & 7, z = tid & 7
-    unsigned long long vlo = 0;   // valid bits of j = 0..11 (5 per j)
-    unsigned vhi = 0;             // j = 12..15
-    int cnt = 0;
-    if (slot >= 0) {
+    // pass 1 (count): list the candidate triangles of the block as (tid << 3 | k) in the reference's slot order.
+    // Reference thread -> voxel mapping (tsdf.cu:903-906) for VPB = 8: tid = j*32 + lane -> x = tid >> 6,
+    // y = ((tid >> 3) - bz) & 7, z = tid & 7.
+    unsigned short* wl = s_list[wid];
+    int nlist = 0;
 #pragma unroll 1
-      for (int j = 0; j < 16; j++) {
-        const int t = j * 32 + lane;
-        const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
-        const int need = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);
-        int cube = 0;
-        if ((okbits >> need) & 1u) cube = cube_index(tile, lx, ly, lz);
-        const bool surf = cube != 0 && cube != 255;
-        if (!__any_sync(0xffffffffu, surf)) continue;
-        unsigned valid = 0;
-        if (surf) {
-          const int ntri = s_ntri[cube];
-          for (int k = 0; k < ntri; k++) {
-            const Vtx p0 = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k], false);
-            const Vtx p1 = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k + 1], false);
-            const Vtx p2 = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k + 2], false);
-            if (!(same_pos(p0, p1) || same_pos(p1, p2))) valid |= 1u << k;     // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
-          }
-        }
-        if (j < 12) vlo |= (unsigned long long)valid << (5 * j); else vhi |= valid << (5 * (j - 12));
-        cnt += __popc(valid);
-      }
-    }
-    int total = cnt;
+    for (int j = 0; j < 16; j++) {
+      const int t = j * 32 + lane;
+      const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
+      const int need = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);
+      int nt = 0;
+      if ((okbits >> need) & 1u) nt = s_ntri[cube_index(tile, lx, ly, lz)];     // 0 for cube index 0 and 255
+      if (!__any_sync(0xffffffffu, nt > 0)) continue;
+      int incl = nt;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      for (int k = 0; k < nt; k++) wl[nlist + incl - nt + k] = (unsigned short)((t << 3) | k);
+      nlist += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
 
+    // one reservation per block for all candidates (the few degenerate ones leave unused arena slots behind the block's range)
     unsigned long long base = 0;
     bool fits = true;
-    if (total > 0) {
+    if (nlist > 0) {
       if (lane == 0) {
-        base = atomicAdd(D.arena_top, (unsigned long long)total);
-        if (base + (unsigned long long)total > D.arena_cap) { atomicOr(D.engine_error, 1); fits = false; }
+        base = atomicAdd(D.arena_top, (unsigned long long)nlist);
+        if (base + (unsigned long long)nlist > D.arena_cap) { atomicOr(D.engine_error, 1); fits = false; }
       }
       base = __shfl_sync(0xffffffffu, base, 0);
       fits = __shfl_sync(0xffffffffu, fits, 0);
     }
-    if (lane == 0 && slot >= 0) { out_offset[slot] = base; out_count[slot] = (total > 0 && fits) ? total : 0; }
 
-    // pass 2: emit in the reference's slot order (tid ascending, k ascending)
-    if (total > 0 && fits) {
-      int running = 0;
-#pragma unroll 1
-      for (int j = 0; j < 16; j++) {
-        const unsigned valid = j < 12 ? (unsigned)((vlo >> (5 * j)) & 31ull) : ((vhi >> (5 * (j - 12))) & 31u);
-        const int c = __popc(valid);
-        if (!__any_sync(0xffffffffu, c > 0)) continue;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (c) {
-          const int t = j * 32 + lane;
+    // pass 2 (emit): one candidate triangle per lane; survivors of the degenerate rule are written compactly, in order
+    int written = 0;
+    if (nlist > 0 && fits) {
+      for (int e0 = 0; e0 < nlist; e0 += 32) {
+        const int e = e0 + lane;
+        bool valid = false;
+        Vtx p0, p1, p2;
+        if (e < nlist) {
+          const int item = wl[e];
+          const int t = item >> 3, k = item & 7;
           const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
-          const int cube = cube_index(tile, lx, ly, lz);
-          unsigned long long pos = base + (unsigned long long)(running + incl - c);
-          for (int k = 0; k < 5; k++) {
-            if (valid & (1u << k)) {
-              uint4* dst = reinterpret_cast<uint4*>(D.arena + pos);
-#pragma unroll
-              for (int m = 0; m < 3; m++) {
-                const Vtx p = edge_vertex(B, D, lx, ly, lz, s_tri[cube * 16 + 3 * k + m], color);
-                dst[m] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), p.c);
-              }
-              ++pos;
-            }
-          }
+          const signed char* row = s_tri + cube_index(tile, lx, ly, lz) * 16 + 3 * k;
+          p0 = edge_vertex(B, D, lx, ly, lz, row[0], color);
+          p1 = edge_vertex(B, D, lx, ly, lz, row[1], color);
+          p2 = edge_vertex(B, D, lx, ly, lz, row[2], color);
+          valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
         }
-        running += __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(D.arena + base + (unsigned long long)(written + __popc(bal & ((1u << lane) - 1))));
+          dst[0] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), p0.c);
+          dst[1] = make_uint4(__float_as_uint(p1.x), __float_as_uint(p1.y), __float_as_uint(p1.z), p1.c);
+          dst[2] = make_uint4(__float_as_uint(p2.x), __float_as_uint(p2.y), __float_as_uint(p2.z), p2.c);
+        }
+        written += __popc(bal);
       }
-      if (lane == 0) my_tris += (unsigned long long)total;
     }
-    __syncwarp();   // the tile is reused by the next block
+    if (lane == 0) { out_offset[slot] = base; out_count[slot] = written; my_tris += (unsigned long long)written; }
+    __syncwarp();   // tile and list are reused by the next block
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
 
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count, int full_map,
                            unsigned long long* out_offset, int* out_count, int num_sms, cudaStream_t st) {
-  marching_cubes_kernel<<<num_sms * 4, MC_THREADS, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count);
+  marching_cubes_kernel<<<num_sms * 10, MC_THREADS, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count);
 }
 
 }  // namespace vh
