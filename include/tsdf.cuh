@@ -1,0 +1,271 @@
+// tsdf.cuh — drop-in for the reference's engine header (/root/reference/include/tsdf.cuh): the same namespace,
+// type names and ark::GpuTsdfGenerator surface (tsdf.cuh:604-643), implemented as a thin host-side C++ wrapper over
+// the C ABI of the B200 engine (include/vh_c.h, libvhsdf.so). A caller such as the reference's
+// PointCloudGenerator.cpp:43,127,154,158 or main.cpp compiles against this header unchanged and links libvhsdf.so
+// instead of libTSDF.so. No CUDA code is needed to include it: plain g++ works (vector types come from
+// cuda_runtime.h's vector_types.h).
+//
+// Differences a maintainer should know (INTEGRATION.md has the full list):
+//   * VOXEL_PER_BLOCK is 8 (the reference macro is 5, tsdf.cuh:40): the engine's block is 8^3.
+//   * The reference's compile-time constants (table shape, DDA stride, ray-step cap, chunk radius, world extent) are
+//     run-time fields of vh_params; GpuTsdfGenerator::Options() exposes them before construction.
+//   * The map lives in HBM for the life of the object: there is no per-frame stream-in / stream-out and no host
+//     Chunk store; getVertices()/getFaces() are filled by SavePLY()/UpdateMesh() instead of staying empty
+//     (tsdf.cu:1947-1960 returns vectors nothing ever writes).
+//   * Errors keep the reference's conventions: a failing CUDA call throws the C string "CUDA Error"
+//     (safecall.cpp:9-28), pool exhaustion throws "out of block memory" (impl/blockalloc.h:51), a full table throws
+//     "Error here!" (vhashing.h:106); nothing spins forever and nothing calls exit().
+#ifndef VH_TSDF_CUH_
+#define VH_TSDF_CUH_
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <list>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "vh_c.h"
+#include "vh_mc_tables.h"
+
+#define T_PER_BLOCK 8
+#define VOXEL_PER_BLOCK 8
+#define BLOCK_PER_CHUNK 8
+#define MAX_CHUNK_NUM 128
+#define CHUNK_RADIUS 4.0
+
+namespace ark {
+
+// 16 bytes, same layout as vh_vertex (tsdf.cuh:65-77)
+struct Vertex {
+  float x, y, z;
+  unsigned char r, g, b;
+  Vertex() {}
+  Vertex(float xi, float yi, float zi) : x(xi), y(yi), z(zi), r(0), g(0), b(0) {}
+};
+inline bool operator==(const Vertex& a, const Vertex& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+
+struct VertexEqual {
+  bool operator()(Vertex a, Vertex b) const { return a == b; }
+};
+struct VertexHasher {            // truncating float -> size_t products xor-ed, as the reference keys its dedupe map (tsdf.cuh:88-99)
+  size_t operator()(Vertex v) const {
+    return ((size_t)v.x * 73856093u) ^ ((size_t)v.y * 19349669u) ^ ((size_t)v.z * 83492791u);
+  }
+};
+
+struct Triangle {
+  Vertex p[3];
+  bool valid;
+  Triangle() : valid(false) {}
+};
+struct Face {
+  int vIdx[3];
+};
+
+struct Voxel {                   // the reference's AoS voxel (tsdf.cuh:120-129); the engine stores SoA planes, this is the exchange format
+  float sdf;
+  unsigned char sdf_color[3];
+  float weight;
+  Voxel() : sdf(0), weight(0) { sdf_color[0] = sdf_color[1] = sdf_color[2] = 0; }
+};
+struct VoxelBlock {
+  Voxel voxels[VOXEL_PER_BLOCK * VOXEL_PER_BLOCK * VOXEL_PER_BLOCK];
+};
+struct VoxelBlockPos {
+  int3 pos;
+  VoxelBlockPos() : pos(make_int3(0, 0, 0)) {}
+};
+
+// API-visible functors of the reference's table instantiation (tsdf.cuh:144-165); the engine's own table uses a
+// different 64-bit mix internally, these are kept for code that names them
+struct BlockHasher {
+  __host__ __device__ size_t operator()(int3 b) const {
+    return ((size_t)(long long)b.x * 73856093ull) ^ ((size_t)(long long)b.y * 19349669ull) ^ ((size_t)(long long)b.z * 83492791ull);
+  }
+};
+struct BlockEqual {
+  __host__ __device__ bool operator()(int3 a, int3 b) const { return a.x == b.x && a.y == b.y && a.z == b.z; }
+};
+
+// scalars of the reference's MarchingCubeParam (tsdf.cuh:220-232); the lookup tables live in vh_mc_tables.h /
+// __constant__ memory instead of inside this struct
+class MarchingCubeParam {
+ public:
+  float3 vox_origin;
+  float vox_size;
+  float trunc_margin;
+  int3 vox_dim;
+  int total_vox;
+  float max_depth;
+  float min_depth;
+  float block_size;
+  int im_width;
+  int im_height;
+  float fx, fy, cx, cy;
+};
+
+class GpuTsdfGenerator {
+ public:
+  // Run-time versions of the reference's macros/literals; edit before constructing an engine.
+  static vh_params& Options() {
+    static vh_params p = [] { vh_params q; vh_default_params(&q); return q; }();
+    return p;
+  }
+
+  GpuTsdfGenerator(int width, int height, float fx, float fy, float cx, float cy, float max_depth, float origin_x = -1.5f,
+                   float origin_y = -1.5f, float origin_z = 0.5f, float vox_size = 0.006f, float trunc_m = 0.03f, int vox_dim_x = 500,
+                   int vox_dim_y = 500, int vox_dim_z = 500) {
+    std::cout << " GpuTsdfGenerator init " << std::endl;
+    vh_params p = Options();
+    p.width = width; p.height = height; p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy;
+    p.max_depth = max_depth; p.vox_size = vox_size; p.trunc_margin = trunc_m;
+    param_.vox_origin = make_float3(origin_x, origin_y, origin_z);      // accepted and ignored by the hash path (tsdf.cu:644-646)
+    param_.vox_dim = make_int3(vox_dim_x, vox_dim_y, vox_dim_z);
+    param_.total_vox = vox_dim_x * vox_dim_y * vox_dim_z;
+    param_.vox_size = vox_size; param_.trunc_margin = trunc_m; param_.max_depth = max_depth; param_.min_depth = p.min_depth;
+    param_.block_size = VOXEL_PER_BLOCK * vox_size;
+    param_.im_width = width; param_.im_height = height; param_.fx = fx; param_.fy = fy; param_.cx = cx; param_.cy = cy;
+    params_ = p;
+    raise(vh_create(&p, &engine_));
+  }
+  GpuTsdfGenerator(const vh_params& p) : params_(p) {
+    std::memset(&param_, 0, sizeof(param_));
+    param_.vox_size = p.vox_size; param_.trunc_margin = p.trunc_margin; param_.max_depth = p.max_depth; param_.min_depth = p.min_depth;
+    param_.block_size = VOXEL_PER_BLOCK * p.vox_size; param_.im_width = p.width; param_.im_height = p.height;
+    param_.fx = p.fx; param_.fy = p.fy; param_.cx = p.cx; param_.cy = p.cy;
+    raise(vh_create(&p, &engine_));
+  }
+  GpuTsdfGenerator(const GpuTsdfGenerator&) = delete;
+  GpuTsdfGenerator& operator=(const GpuTsdfGenerator&) = delete;
+  ~GpuTsdfGenerator() { Shutdown(); }
+
+  // depth: float[H*W] metres (0 = invalid); rgb: uchar[H*W*3] RGB; c2w: float[16] row-major camera->world. Host
+  // pointers borrowed for the call; synchronous like the reference (tsdf.cu:1485-1598).
+  void processFrame(float* depth, unsigned char* rgb, float* c2w) {
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    raise(vh_integrate(engine_, depth, rgb, c2w));
+  }
+  // the same frame without waiting for the GPU; call Sync() before reading results or reusing the buffers
+  void processFrameAsync(const float* depth, const unsigned char* rgb, const float* c2w) {
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    raise(vh_integrate_async(engine_, depth, rgb, c2w));
+  }
+  void Sync() { raise(vh_sync(engine_)); }
+
+  void getLocalGrid() {}
+  void insert_tri() {}
+
+  // Immediate-mode GL drawing of the reference (tsdf.cu:1711-1758) is a viewer concern: without GL headers this is
+  // a no-op that only refreshes the CPU-side mesh; define VH_WITH_GL before including to draw.
+  void render() {
+#ifdef VH_WITH_GL
+    UpdateMesh();
+    std::unique_lock<std::mutex> lock(tri_mutex_);
+    glBegin(GL_TRIANGLES);
+    for (const Face& f : global_face)
+      for (int j = 0; j < 3; j++) {
+        const Vertex& v = global_vertex[f.vIdx[j]];
+        glColor3f(v.r / 255.f, v.g / 255.f, v.b / 255.f);
+        glVertex3f(v.x, v.y, v.z);
+      }
+    glEnd();
+#endif
+  }
+
+  void Shutdown() {
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    if (engine_) { vh_destroy(engine_); engine_ = nullptr; }
+  }
+
+  // The reference's SaveTSDF dumps a legacy dense grid through host arrays it never allocates (tsdf.cu:1663-1694,
+  // :1336-1341). Here: 8-float header (dims = block count, 1, 1; origin; voxel size; truncation) followed by, per
+  // allocated block, its int3 key and the 512 sdf values and 512 weights.
+  void SaveTSDF(std::string filename) {
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    int n = 0;
+    raise(vh_allocated_keys(engine_, nullptr, 0, &n));
+    std::vector<int32_t> keys((size_t)(n > 0 ? n : 1) * 3);
+    raise(vh_allocated_keys(engine_, keys.data(), n, &n));
+    std::vector<float> sdf((size_t)n * 512), w((size_t)n * 512);
+    std::vector<uint8_t> found((size_t)n);
+    raise(vh_download_blocks(engine_, keys.data(), n, sdf.data(), w.data(), nullptr, found.data()));
+    FILE* f = std::fopen(filename.c_str(), "wb");
+    if (!f) throw "CUDA Error";
+    const float head[8] = {(float)n, 1.f, 1.f, param_.vox_origin.x, param_.vox_origin.y, param_.vox_origin.z, param_.vox_size, param_.trunc_margin};
+    std::fwrite(head, sizeof(float), 8, f);
+    for (int i = 0; i < n; i++) {
+      std::fwrite(&keys[3 * (size_t)i], sizeof(int32_t), 3, f);
+      std::fwrite(&sdf[(size_t)i * 512], sizeof(float), 512, f);
+      std::fwrite(&w[(size_t)i * 512], sizeof(float), 512, f);
+    }
+    std::fclose(f);
+  }
+
+  // ASCII PLY with exact-xyz vertex dedupe, vertices * vox_size (tsdf2mesh, tsdf.cu:1760-1888)
+  void SavePLY(std::string filename) {
+    UpdateMesh();
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    raise(vh_save_ply(engine_, filename.c_str(), mesh_mode_));
+    std::cout << "vertex size " << global_vertex.size() << std::endl << "face size " << global_face.size() << std::endl;
+  }
+
+  // refresh getVertices()/getFaces() from the map (welded mesh, world units)
+  void UpdateMesh() {
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    uint64_t nv = 0, nf = 0;
+    raise(vh_weld_mesh(engine_, mesh_mode_, nullptr, 0, &nv, nullptr, 0, &nf));
+    std::vector<vh_vertex> v((size_t)(nv ? nv : 1));
+    std::vector<int32_t> f((size_t)(nf ? nf : 1) * 3);
+    raise(vh_weld_mesh(engine_, mesh_mode_, v.data(), nv, &nv, f.data(), nf, &nf));
+    std::unique_lock<std::mutex> tlock(tri_mutex_);
+    global_vertex.resize((size_t)nv);
+    global_face.resize((size_t)nf);
+    static_assert(sizeof(Vertex) == sizeof(vh_vertex), "Vertex layout");
+    if (nv) std::memcpy(global_vertex.data(), v.data(), (size_t)nv * sizeof(vh_vertex));
+    if (nf) std::memcpy(global_face.data(), f.data(), (size_t)nf * sizeof(Face));
+  }
+  void SetMeshMode(int mode) { mesh_mode_ = mode; }     // VH_MESH_REF_PERSISTENT (reference semantics) or VH_MESH_FULL_MAP
+
+  std::vector<Vertex>* getVertices() { return &global_vertex; }
+  std::vector<Face>* getFaces() { return &global_face; }
+  std::vector<std::list<std::pair<Vertex, int>>>* getHashMap() { return &global_map; }
+  MarchingCubeParam* getMarchingCubeParam() { return &param_; }
+
+  // index of vertex p in getVertices() or -1 (the reference's spatial-grid lookup, tsdf.cu:1890-1945, as a scan)
+  int find_vertex(Vertex p, uint3 /*grid_size*/, float /*cell_size*/, std::vector<std::list<std::pair<Vertex, int>>>& /*hash_table*/) {
+    for (size_t i = 0; i < global_vertex.size(); i++)
+      if (global_vertex[i] == p) return (int)i;
+    return -1;
+  }
+
+  // engine-level extras
+  vh_engine* handle() const { return engine_; }
+  vh_stats stats() { vh_stats s; raise(vh_get_stats(engine_, &s)); return s; }
+  const vh_params& params() const { return params_; }
+
+ private:
+  void raise(int rc) const {
+    if (rc == VH_OK) return;
+    std::cerr << "GpuTsdfGenerator: " << vh_last_error() << std::endl;
+    if (rc == VH_ERR_POOL_FULL) throw "out of block memory";
+    if (rc == VH_ERR_TABLE_FULL) throw "Error here!";
+    throw "CUDA Error";
+  }
+
+  vh_engine* engine_ = nullptr;
+  vh_params params_;
+  MarchingCubeParam param_;
+  int mesh_mode_ = VH_MESH_REF_PERSISTENT;
+  std::mutex tri_mutex_, tsdf_mutex_;
+  std::vector<Vertex> global_vertex;
+  std::vector<Face> global_face;
+  std::vector<std::list<std::pair<Vertex, int>>> global_map;
+};
+
+}  // namespace ark
+#endif  // VH_TSDF_CUH_

@@ -1,4 +1,4 @@
-// vh_map.cuh — lock-free spatial hash of voxel-block coordinates (device side).
+// vh_map.cuh — lock-free spatial hash of voxel-block coordinates (device side). Public: include/vhashing.h builds on it.
 //
 // Replaces the reference's bucketed table with per-bucket spin locks
 // (/root/reference/include/vhashing.h:140-239 tryfind/operator[], :395-484 real_insert,

@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #include "../../include/vh_c.h"
-#include "vh_map.cuh"
+#include "../../include/vh_map.cuh"
 
 namespace vh {
 

@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "../../include/vh_c.h"
-#include "vh_map.cuh"
+#include "../../include/vh_map.cuh"
 
 using namespace vh;
 
