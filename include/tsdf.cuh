@@ -226,7 +226,7 @@ class GpuTsdfGenerator {
     global_vertex.resize((size_t)nv);
     global_face.resize((size_t)nf);
     static_assert(sizeof(Vertex) == sizeof(vh_vertex), "Vertex layout");
-    if (nv) std::memcpy(global_vertex.data(), v.data(), (size_t)nv * sizeof(vh_vertex));
+    if (nv) std::memcpy((void*)global_vertex.data(), v.data(), (size_t)nv * sizeof(vh_vertex));
     if (nf) std::memcpy(global_face.data(), f.data(), (size_t)nf * sizeof(Face));
   }
   void SetMeshMode(int mode) { mesh_mode_ = mode; }     // VH_MESH_REF_PERSISTENT (reference semantics) or VH_MESH_FULL_MAP
