@@ -195,7 +195,7 @@ def run_ours(args):
 
     p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"],
                             num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=3 << 20,
-                            use_color=1 if color else 0, mc_per_frame=0 if args.no_mc else 1, device=local, tri_arena_bytes=8 << 30)
+                            use_color=1 if color else 0, mc_per_frame=0 if args.no_mc else 1, device=local, tri_arena_bytes=4 << 30)
     eng = vh.TsdfEngine(p)
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
     dptr = lambda t, i: t[i].data_ptr()
@@ -273,7 +273,8 @@ def run_ours(args):
         acc["alloc"] += s.ms_alloc; acc["integrate"] += s.ms_integrate; acc["mc"] += s.ms_mc
         acc["updates"] += s.voxel_updates; acc["visible"] += s.visible_blocks; acc["tris"] += s.triangles
     clocks = sampler.stop() if sampler else None
-    allocated = eng.stats().allocated_blocks
+    st_last = eng.stats()
+    allocated = st_last.allocated_blocks
 
     total_frames = sum_over_ranks(float(n_timed))
     value = total_frames / (ms_value / 1000.0)
@@ -305,7 +306,8 @@ def run_ours(args):
         "gpu_launches": 3 * n_timed if not args.no_mc else 2 * n_timed,
         "voxel_updates_per_sec": sum_over_ranks(float(acc["updates"])) / (ms_value / 1000.0),
         "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "triangles": tris_per_frame,
-                      "ms_alloc": ms_alloc, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated},
+                      "ms_alloc": ms_alloc, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated,
+                      "arena_compactions_in_500_frames": int(st_last.arena_compactions)},
         "roofline": {"kernel": "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": None,
                      "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int},

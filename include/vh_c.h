@@ -67,7 +67,8 @@ typedef struct vh_params {
   int device;                   /* CUDA device ordinal                                                         */
   int shard_rank, shard_count;  /* multi-GPU: this engine owns blocks with owner(key) == shard_rank            */
   int depth_tile_smem;          /* 1: stage per-block depth tiles through TMA/shared memory in integrate       */
-  uint64_t tri_arena_bytes;     /* initial triangle arena size (grows on demand); 0 = default                  */
+  uint64_t tri_arena_bytes;     /* triangle arena size (grows on demand); 0 = default 1 GiB. With mc_per_frame a
+                                   second arena of the same size is held as the compaction target                */
 } vh_params;
 
 typedef struct vh_stats {
@@ -80,6 +81,7 @@ typedef struct vh_stats {
   uint64_t arena_triangles;     /* triangles currently held in the arena (live + superseded) */
   float ms_upload, ms_alloc, ms_integrate, ms_mc;   /* CUDA-event times of the last frame's stages */
   uint64_t debug_mismatches;    /* with env VH_INTEGRATE_VERIFY=1: fast-path vs IEEE-path disagreements in the last frame (must be 0) */
+  uint64_t arena_compactions;   /* times the triangle arena was compacted (superseded per-block meshes dropped) */
 } vh_stats;
 
 /* vertex layout of the triangle soup: the reference's Vertex (tsdf.cuh:65-77), 16 bytes */

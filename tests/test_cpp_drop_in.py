@@ -79,7 +79,7 @@ def test_gpu_tsdf_generator_drop_in(vh, ob, synth, tmp_path):
     uniq = np.unique(xyz.reshape(-1, 3), axis=0)
     assert len(verts) == len(uniq)
     soup = xyz.reshape(-1, 3) * np.float32(kw["vox_size"])
-    assert np.allclose(verts[faces.reshape(-1), :3], soup, rtol=2e-6, atol=1e-7)
+    assert np.allclose(verts[faces.reshape(-1), :3], soup, rtol=1e-5, atol=1e-7)       # the PLY is ASCII at 6 significant digits
     m = re.search(r"vertices (\d+) faces (\d+)", out.stdout)
     assert (int(m.group(1)), int(m.group(2))) == (len(verts), len(faces))
 
@@ -111,5 +111,5 @@ def test_headless_load_frames(vh, ob, synth, tmp_path):
     xyz, _ = o.triangles()
     verts, faces = read_ply(ply)
     assert len(faces) == len(xyz) > 0
-    assert np.allclose(verts[faces.reshape(-1), :3], xyz.reshape(-1, 3) * np.float32(0.04), rtol=2e-6, atol=1e-7)
+    assert np.allclose(verts[faces.reshape(-1), :3], xyz.reshape(-1, 3) * np.float32(0.04), rtol=1e-5, atol=1e-7)       # the PLY is ASCII at 6 significant digits
     assert f"allocated blocks {len(o.all_keys())}" in out.stdout

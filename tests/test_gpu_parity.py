@@ -93,6 +93,14 @@ def test_engine_matches_oracle_640x480_5mm_color(vh, ob, synth):
     run_pair(vh, ob, sc, case, frames=3, num_buckets=1 << 20, pool_blocks=1 << 19, tri_arena_bytes=512 << 20)
 
 
+def test_engine_matches_oracle_5mm_sequence(vh, ob, synth):
+    """40 consecutive frames of the headline config (the bench workload): per-frame visible set, voxel updates and
+    working-set triangle count, then every voxel and the final ordered mesh."""
+    sc = synth.make_scene("C2", color=True)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.005, trunc=0.025, max_depth=10.0)
+    run_pair(vh, ob, sc, case, frames=40, num_buckets=1 << 20, pool_blocks=1 << 19, tri_arena_bytes=2 << 30)
+
+
 def test_engine_matches_oracle_revisit_many_frames(vh, ob, synth):
     """20 frames over a short loop: blocks are re-integrated (weights > 1, harmonic sdf growth) and
     re-meshed ('last frame that saw the block wins', tsdf.cu:534-540)."""

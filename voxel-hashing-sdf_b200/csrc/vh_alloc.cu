@@ -6,11 +6,11 @@
 //   HashAssignKernel                         (tsdf.cu:2088-2238)  -> same rays, same 3-D DDA, same frustum test;
 //   getHeapCounterKernel + 4 memcpys         (tsdf.cu:2244-2251, :2318-2337) -> a device-side counter.
 //
-// Shape: one CTA owns a tile of 8x4 sampled pixels (32 rays).
-//   Phase A  32 lanes march their rays through the block grid (pure ALU, sequential per ray because the
+// Shape: one CTA owns a tile of 4x2 sampled pixels (8 rays); small tiles keep every SM busy (3,072 rays in all).
+//   Phase A  8 lanes march their rays through the block grid (pure ALU, sequential per ray because the
 //            reference accumulates tmax by repeated float addition) and drop the visited block keys into
 //            shared memory, keys[step][ray].
-//   Phase B  all 8 warps sweep that list; a warp sees the 32 neighbouring rays of one step, so equal keys are
+//   Phase B  all 8 warps sweep that list; a warp sees the 8 neighbouring rays of 4 consecutive steps, so equal keys are
 //            folded with __match_any_sync, the group leader claims the entry with one 64-bit atomicCAS,
 //            pool slots for new blocks are popped with one atomicSub per warp (ballot/popc ranks), and blocks
 //            first seen this frame (atomicExch on the entry's frame stamp) are compacted into the visible list
@@ -20,7 +20,7 @@
 
 namespace vh {
 
-constexpr int RAYS_X = 8, RAYS_Y = 4, RAYS = RAYS_X * RAYS_Y;
+constexpr int RAYS_X = 4, RAYS_Y = 2, RAYS = RAYS_X * RAYS_Y;   // 8 rays per CTA: 384 CTAs at 640x480 / stride 10, ~3 key rounds each
 constexpr int ALLOC_THREADS = 256;
 
 // chunk membership of the reference's stream-in stage

@@ -58,15 +58,19 @@ struct vh_engine {
   const uint8_t* cur_rgb = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // pinned read-back block: counters of the last frame + flags
-  struct HostBlock { FrameCounters c; int map_error; int engine_error; int heap_counter; int pad; unsigned long long arena_top; };
+  typedef DeviceStatus HostBlock;
   HostBlock* h_block = nullptr;
-  int* d_flags = nullptr;               // [0] map error, [1] engine error
+  DeviceStatus* d_status = nullptr;     // counters, error flags, heap counter, arena top: one block, one read-back copy
   uint64_t frames = 0, updates_total = 0;
   uint64_t max_tris_per_frame = 0, known_arena_top = 0;
   int frames_in_flight = 0;
   // full-map extraction scratch
   int* d_full_list = nullptr; int* d_full_count = nullptr; unsigned long long* d_full_off = nullptr; int* d_full_cnt = nullptr;
   u64* d_keys_tmp = nullptr; size_t keys_tmp_cap = 0;
+  // arena compaction: spare arena (ping-pong) and scan scratch
+  vh_triangle* arena_spare = nullptr;
+  unsigned long long *d_scan_in = nullptr, *d_scan_out = nullptr; void* d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+  uint64_t compactions = 0;
   std::mutex mtx;
 };
 
@@ -130,8 +134,9 @@ static int free_engine(vh_engine* e) {
   if (e->upload) cudaStreamSynchronize(e->upload);
   DeviceView& D = e->D;
   cudaFree(D.map.keys); cudaFree(D.map.slots); cudaFree(D.map.free_list); cudaFree(D.map.free_top); cudaFree(D.map.key_heap);
-  cudaFree(D.map.heap_counter); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.visible);
-  cudaFree(D.counters); cudaFree(D.arena); cudaFree(D.arena_top); cudaFree(D.tri_offset); cudaFree(D.tri_count); cudaFree(e->d_flags);
+  cudaFree(e->d_status); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.neg_count); cudaFree(D.visible);
+  cudaFree(D.arena); cudaFree(e->arena_spare); cudaFree(e->d_scan_in); cudaFree(e->d_scan_out); cudaFree(e->d_scan_tmp);
+  cudaFree(D.tri_offset); cudaFree(D.tri_count);
   cudaFree(e->d_full_list); cudaFree(e->d_full_count); cudaFree(e->d_full_off); cudaFree(e->d_full_cnt); cudaFree(e->d_keys_tmp);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_depth[i]); cudaFree(e->d_rgb[i]); cudaFree(e->d_px[i]);
@@ -161,16 +166,14 @@ static int reset_map(vh_engine* e) {
   CK(cudaMemsetAsync(D.sdf, 0, (size_t)nb * BLOCK_VOX * sizeof(float), e->stream));      // Voxel(): sdf = 0, weight = 0 (tsdf.cuh:126-128)
   CK(cudaMemsetAsync(D.wgt, 0, (size_t)nb * BLOCK_VOX * sizeof(float), e->stream));
   if (D.rgb) CK(cudaMemsetAsync(D.rgb, 0, (size_t)nb * BLOCK_VOX * sizeof(uchar4), e->stream));
+  CK(cudaMemsetAsync(D.neg_count, 0, (size_t)nb * sizeof(int), e->stream));
   CK(cudaMemsetAsync(D.tri_offset, 0, (size_t)nb * sizeof(unsigned long long), e->stream));
   CK(cudaMemsetAsync(D.tri_count, 0, (size_t)nb * sizeof(int), e->stream));
-  CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
-  CK(cudaMemsetAsync(D.arena_top, 0, sizeof(unsigned long long), e->stream));
-  CK(cudaMemsetAsync(D.map.heap_counter, 0, sizeof(int), e->stream));
-  CK(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
+  CK(cudaMemsetAsync(e->d_status, 0, sizeof(DeviceStatus), e->stream));
   init_free_list_kernel<<<(nb + 255) / 256, 256, 0, e->stream>>>(D.map.free_list, nb);
   CK(cudaMemcpyAsync(D.map.free_top, &nb, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0;
+  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0;
   memset(e->h_block, 0, sizeof(*e->h_block));
   return VH_OK;
 }
@@ -183,6 +186,8 @@ int vh_create(const vh_params* p, vh_engine** out) {
       p->blocks_per_chunk <= 0 || p->num_buckets <= 0 || p->entries_per_bucket <= 0 || p->pool_blocks <= 0 || p->shard_count <= 0 ||
       p->shard_rank < 0 || p->shard_rank >= p->shard_count)
     return fail(VH_ERR_INVALID, "invalid parameter value");
+  if (!(p->trunc_margin > 1e-15f && p->trunc_margin < 1e15f && p->vox_size > 1e-15f && p->vox_size < 1e15f))
+    return fail(VH_ERR_INVALID, "trunc_margin / vox_size outside the range the integrate kernel's divisions are validated for");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(VH_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
   if (p->device < 0 || p->device >= ndev) return fail(VH_ERR_INVALID, "device %d out of range (%d devices)", p->device, ndev);
@@ -207,9 +212,11 @@ int vh_create(const vh_params* p, vh_engine** out) {
   S.nry = std::min(gy, (p->height + p->dda_stride - 1) / p->dda_stride);
   S.use_color = p->use_color ? 1 : 0;
   S.shard_rank = (uint32_t)p->shard_rank; S.shard_count = (uint32_t)p->shard_count;
-  // approximate-projection error is < 7e-7 * |pixel coordinate| (vh_integrate.cu); 2e-3 px covers images up to ~2000 px
-  S.round_eps = std::max(2e-3f, 1e-3f + 1e-6f * (float)std::max(p->width, p->height));
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
+  { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '2' && v[0] <= '4') ? v[0] - '0' : 4; }   // tuning knobs
+  { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
+  // approximate-projection error bound (vh_integrate.cu, gate4): 6.9e-7 px per pixel of image extent
+  S.round_eps = 7.5e-7f * (float)std::max(p->width, p->height) + 2e-5f;
 
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket;
   uint64_t cap = 1024;
@@ -235,15 +242,14 @@ int vh_create(const vh_params* p, vh_engine** out) {
   ALLOC(D.map.free_list, nb * sizeof(int));
   ALLOC(D.map.free_top, sizeof(int));
   ALLOC(D.map.key_heap, nb * sizeof(u64));
-  ALLOC(D.map.heap_counter, sizeof(int));
-  ALLOC(e->d_flags, 2 * sizeof(int));
+  ALLOC(e->d_status, sizeof(DeviceStatus));
   ALLOC(D.sdf, nb * BLOCK_VOX * sizeof(float));
   ALLOC(D.wgt, nb * BLOCK_VOX * sizeof(float));
   if (S.use_color) ALLOC(D.rgb, nb * BLOCK_VOX * sizeof(uchar4));
+  ALLOC(D.neg_count, nb * sizeof(int));
   ALLOC(D.visible, (size_t)D.list_cap * sizeof(int));
-  ALLOC(D.counters, sizeof(FrameCounters));
   ALLOC(D.arena, D.arena_cap * sizeof(vh_triangle));
-  ALLOC(D.arena_top, sizeof(unsigned long long));
+  if (p->mc_per_frame) ALLOC(e->arena_spare, D.arena_cap * sizeof(vh_triangle));      // compaction target; the two swap roles
   ALLOC(D.tri_offset, nb * sizeof(unsigned long long));
   ALLOC(D.tri_count, nb * sizeof(int));
   const size_t npx = (size_t)p->width * p->height;
@@ -255,8 +261,12 @@ int vh_create(const vh_params* p, vh_engine** out) {
 #undef ALLOC
   D.map.mask = e->capacity - 1;
   D.map.num_blocks = p->pool_blocks;
-  D.map.error_flag = e->d_flags;
-  D.engine_error = e->d_flags + 1;
+  D.counters = &e->d_status->c;
+  D.map.error_flag = &e->d_status->map_error;
+  D.engine_error = &e->d_status->engine_error;
+  D.map.heap_counter = &e->d_status->heap_counter;
+  D.overflow_frame = &e->d_status->overflow_frame;
+  D.arena_top = &e->d_status->arena_top;
   bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->upload, cudaStreamNonBlocking) == cudaSuccess &&
             cudaHostAlloc((void**)&e->h_block, sizeof(*e->h_block), cudaHostAllocDefault) == cudaSuccess;
@@ -298,17 +308,20 @@ __global__ void widen_counts_kernel(const int* cnt, unsigned long long* out, int
 }
 
 // Drop superseded triangles (blocks re-meshed in later frames) and make room for `need` more. Stream must be idle.
+// The live ranges are copied into the spare arena (same size, allocated with the engine) and the two swap roles, so a
+// steady-state compaction allocates nothing; only growth (live set above half an arena) reallocates.
 static int compact_arena(vh_engine* e, unsigned long long need) {
   DeviceView& D = e->D;
   const int nb = e->P.pool_blocks;
-  unsigned long long *d_wide = nullptr, *d_new = nullptr;
-  void* d_tmp = nullptr; size_t tmp_bytes = 0;
-  CK(cudaMalloc(&d_wide, (size_t)nb * sizeof(unsigned long long)));
-  CK(cudaMalloc(&d_new, ((size_t)nb + 1) * sizeof(unsigned long long)));
+  if (!e->d_scan_in) {
+    CK(cudaMalloc((void**)&e->d_scan_in, (size_t)nb * sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&e->d_scan_out, ((size_t)nb + 1) * sizeof(unsigned long long)));
+    cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_scan_in, e->d_scan_out, nb, e->stream);
+    CK(cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes));
+  }
+  unsigned long long *d_wide = e->d_scan_in, *d_new = e->d_scan_out;
   widen_counts_kernel<<<(nb + 255) / 256, 256, 0, e->stream>>>(D.tri_count, d_wide, nb);
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_new, nb, e->stream);
-  CK(cudaMalloc(&d_tmp, tmp_bytes));
-  cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wide, d_new, nb, e->stream);
+  cub::DeviceScan::ExclusiveSum(e->d_scan_tmp, e->scan_tmp_bytes, d_wide, d_new, nb, e->stream);
   unsigned long long last_off = 0, last_cnt = 0;
   CK(cudaMemcpyAsync(&last_off, d_new + nb - 1, sizeof(last_off), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(&last_cnt, d_wide + nb - 1, sizeof(last_cnt), cudaMemcpyDeviceToHost, e->stream));
@@ -317,27 +330,36 @@ static int compact_arena(vh_engine* e, unsigned long long need) {
   unsigned long long new_cap = D.arena_cap;
   while (live + need > new_cap / 2) new_cap *= 2;      // keep at least half the arena free after compaction
   vh_triangle* fresh = nullptr;
-  cudaError_t ce = cudaMalloc((void**)&fresh, new_cap * sizeof(vh_triangle));
-  if (ce != cudaSuccess) { cudaFree(d_wide); cudaFree(d_new); cudaFree(d_tmp); return fail(VH_ERR_ARENA_FULL, "triangle arena cannot grow to %llu triangles: %s", new_cap, cudaGetErrorString(ce)); }
+  if (new_cap == D.arena_cap && e->arena_spare) {
+    fresh = e->arena_spare;
+    e->arena_spare = nullptr;
+  } else {
+    cudaFree(e->arena_spare); e->arena_spare = nullptr;
+    cudaError_t ce = cudaMalloc((void**)&fresh, new_cap * sizeof(vh_triangle));
+    if (ce != cudaSuccess) return fail(VH_ERR_ARENA_FULL, "triangle arena cannot grow to %llu triangles: %s", new_cap, cudaGetErrorString(ce));
+  }
   compact_copy_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(D.arena, fresh, D.tri_offset, d_new, D.tri_count, nb);
   CK(cudaMemcpyAsync(D.tri_offset, d_new, (size_t)nb * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(D.arena_top, &live, sizeof(live), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  cudaFree(D.arena); cudaFree(d_wide); cudaFree(d_new); cudaFree(d_tmp);
+  if (new_cap == D.arena_cap) e->arena_spare = D.arena;     // the old arena becomes the spare
+  else {
+    cudaFree(D.arena);
+    if (cudaMalloc((void**)&e->arena_spare, new_cap * sizeof(vh_triangle)) != cudaSuccess) { e->arena_spare = nullptr; cudaGetLastError(); }   // next compaction allocates
+  }
   D.arena = fresh; D.arena_cap = new_cap;
   e->known_arena_top = live;
+  e->compactions++;
   return VH_OK;
 }
 
 // ---- frame pipeline -----------------------------------------------------------------------------
 static int enqueue_stages(vh_engine* e, bool do_alloc) {
   DeviceView& D = e->D;
-  if (do_alloc) {
-    CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
-    launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
-  }
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
-  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, e->stream);
+  // first kernel of the frame: packs {depth, rgb} records for integrate and resets the frame's counters
+  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
+  if (do_alloc) launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
   CK(cudaEventRecord(e->ev[2], e->stream));
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[3], e->stream));
@@ -349,10 +371,8 @@ static int enqueue_stages(vh_engine* e, bool do_alloc) {
 
 static int enqueue_readback(vh_engine* e) {
   DeviceView& D = e->D;
-  CK(cudaMemcpyAsync(&e->h_block->c, D.counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(&e->h_block->map_error, e->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(&e->h_block->heap_counter, D.map.heap_counter, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(&e->h_block->arena_top, D.arena_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  (void)D;
+  CK(cudaMemcpyAsync(e->h_block, e->d_status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, e->stream));
   return VH_OK;
 }
 
@@ -364,13 +384,18 @@ static int finish_sync(vh_engine* e) {
   e->max_tris_per_frame = std::max<uint64_t>(e->max_tris_per_frame, hb->c.triangles);
   if (hb->map_error & MAP_TABLE_FULL) return fail(VH_ERR_TABLE_FULL, "hash table full (%u entries): raise num_buckets/entries_per_bucket", e->capacity);
   if (hb->map_error & MAP_POOL_FULL) return fail(VH_ERR_POOL_FULL, "out of block memory: pool of %d voxel blocks exhausted, raise pool_blocks", e->P.pool_blocks);
+  if (hb->engine_error & 2) return fail(VH_ERR_CUDA, "CUDA Error: integrate met a value outside the validated range of its division sequence");
   if (hb->engine_error & 1) {
-    // the last frame's marching cubes ran out of arena: compact/grow, then redo it (it only reads voxels + stamps)
-    int zero = 0;
-    CK(cudaMemcpyAsync(e->D.engine_error, &zero, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    // marching cubes ran out of arena. Compact/grow; if only the last frame was hit, redo it (it only reads voxels + stamps).
+    const uint32_t first_bad = hb->overflow_frame, last = e->F.frame;
+    CK(cudaMemsetAsync(e->D.engine_error, 0, 2 * sizeof(int), e->stream));      // engine_error + overflow_frame are adjacent
     CK(cudaStreamSynchronize(e->stream));
     int rc = compact_arena(e, std::max<unsigned long long>(hb->c.triangles * 2, 1ull << 20));
     if (rc != VH_OK) return rc;
+    if (first_bad != last)
+      return fail(VH_ERR_ARENA_FULL, "triangle arena overflowed in frame %u while frames up to %u were in flight: blocks meshed in between are "
+                  "incomplete until seen again; raise tri_arena_bytes or call vh_sync more often (arena grown to %llu triangles)",
+                  first_bad, last, (unsigned long long)e->D.arena_cap);
     CK(cudaMemsetAsync(&e->D.counters->triangles, 0, sizeof(unsigned long long), e->stream));
     launch_marching_cubes(e->S, e->F, e->D, e->D.visible, &e->D.counters->visible_count, 0, e->D.tri_offset, e->D.tri_count, e->num_sms, e->stream);
     rc = enqueue_readback(e);
@@ -382,12 +407,19 @@ static int finish_sync(vh_engine* e) {
   return VH_OK;
 }
 
-// keep enough arena head-room for the frames that will be in flight before the next sync
+// Keep enough arena head-room for the frames that are in flight. The pinned status block is refreshed by every
+// frame's read-back copy, so it can be read without a sync: it tells which frame has completed, where the arena top
+// was then and how many triangles a frame produces.
 static int make_room(vh_engine* e) {
   if (!e->P.mc_per_frame) return VH_OK;
+  const volatile DeviceStatus* hb = e->h_block;
+  const uint64_t seen_frame = hb->c.frame, seen_top = hb->arena_top, seen_tris = hb->c.triangles;
+  e->max_tris_per_frame = std::max<uint64_t>(e->max_tris_per_frame, seen_tris);
+  const uint64_t top = std::max<uint64_t>(e->known_arena_top, seen_top);
+  const uint64_t behind = e->frames > seen_frame ? e->frames - seen_frame : 0;           // enqueued, not known to be complete
   const unsigned long long per_frame = std::max<unsigned long long>(e->max_tris_per_frame * 2, 1ull << 18);
-  const unsigned long long projected = e->known_arena_top + per_frame * (unsigned long long)(e->frames_in_flight + 2);
-  if (projected <= e->D.arena_cap) return VH_OK;
+  const unsigned long long projected = top + per_frame * (unsigned long long)(behind + 2);
+  if (projected <= e->D.arena_cap && behind < 256) return VH_OK;
   CK(cudaStreamSynchronize(e->stream));
   int rc = finish_sync(e);
   if (rc != VH_OK) return rc;
@@ -509,7 +541,7 @@ int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb)
   e->S.use_color = e->cur_rgb ? keep : 0;
   CK(cudaMemsetAsync(&e->D.counters->voxel_updates, 0, sizeof(unsigned long long), e->stream));
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
-  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, e->stream);
+  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, nullptr, e->F.frame, e->stream);
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, e->D, e->num_sms, e->stream);
   e->S.use_color = keep;
   int rc = enqueue_readback(e);
@@ -582,6 +614,7 @@ int vh_get_stats(vh_engine* e, vh_stats* out) {
   out->triangles = e->h_block->c.triangles;
   out->arena_triangles = e->h_block->arena_top;
   out->debug_mismatches = e->h_block->c.pad[0];
+  out->arena_compactions = e->compactions;
   if (e->frames > 0) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) out->ms_upload = ms;
@@ -713,22 +746,23 @@ static int collect_blocks(vh_engine* e, int mode, MeshBlocks& mb) {
     }
     // marching cubes over every allocated block into a scratch arena; grow until it fits
     unsigned long long cap = std::max<unsigned long long>(1ull << 20, D.arena_cap / 4);
-    unsigned long long* d_top = nullptr;
-    CK(cudaMalloc((void**)&d_top, sizeof(unsigned long long)));
+    unsigned long long* d_top = nullptr;   // scratch arena top + {engine_error, overflow_frame} for this pass
+    CK(cudaMalloc((void**)&d_top, 2 * sizeof(unsigned long long)));
+    int* d_err = reinterpret_cast<int*>(d_top + 1);
     for (;;) {
       CK(cudaMalloc((void**)&mb.tmp_arena, cap * sizeof(vh_triangle)));
       DeviceView V = D;
       V.arena = mb.tmp_arena; V.arena_cap = cap; V.arena_top = d_top; V.list_cap = nb;
-      CK(cudaMemsetAsync(d_top, 0, sizeof(unsigned long long), e->stream));
+      V.engine_error = d_err; V.overflow_frame = reinterpret_cast<uint32_t*>(d_err + 1);
+      CK(cudaMemsetAsync(d_top, 0, 2 * sizeof(unsigned long long), e->stream));
       CK(cudaMemsetAsync(e->d_full_cnt, 0, (size_t)nb * sizeof(int), e->stream));
       launch_list_all_blocks(D, e->d_full_list, e->d_full_count, e->stream);
       launch_marching_cubes(e->S, e->F, V, e->d_full_list, e->d_full_count, 1, e->d_full_off, e->d_full_cnt, e->num_sms, e->stream);
-      unsigned long long top = 0; int err = 0, zero = 0;
+      unsigned long long top = 0; int err = 0;
       CK(cudaMemcpyAsync(&top, d_top, sizeof(top), cudaMemcpyDeviceToHost, e->stream));
-      CK(cudaMemcpyAsync(&err, D.engine_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
       CK(cudaStreamSynchronize(e->stream));
       if (!(err & 1)) break;
-      CK(cudaMemcpy(D.engine_error, &zero, sizeof(int), cudaMemcpyHostToDevice));
       cudaFree(mb.tmp_arena); mb.tmp_arena = nullptr;
       cap = std::max(cap * 2, top + (top >> 2));
     }

@@ -8,6 +8,7 @@
 //   sdf        f32 [pool_blocks*512] TSDF plane,   voxel index (x*8+y)*8+z    2 KB/block
 //   wgt        f32 [pool_blocks*512] weight plane                             2 KB/block
 //   rgb        u8x4[pool_blocks*512] colour plane (only when use_color)       2 KB/block
+//   neg_count  i32 [pool_blocks]     voxels with sdf < 0 in the block: lets marching cubes skip one-sign neighbourhoods
 //   visible    i32 [list_cap]        entry indices of the frame's visible set (compacted)
 //   tri_arena  48 B triangles, bump-allocated per block per frame; tri_offset/tri_count per pool slot
 #pragma once
@@ -34,6 +35,8 @@ struct StaticParams {
   uint32_t shard_rank, shard_count;
   float round_eps;                // distance from a .5 pixel tie below which integrate re-projects with IEEE divisions
   int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
+  int integrate_two_steps;        // tuning: 1 = gate/load/update two steps of a block together, 0 = one step at a time (default)
+  int integrate_ctas_per_sm;      // resident 256-thread CTAs per SM the integrate kernel is compiled for (2, 3 or 4; default 4)
 };
 
 struct FrameParams {
@@ -44,12 +47,24 @@ struct FrameParams {
   uint32_t frame;                 // 1-based frame stamp
 };
 
-// per-frame device counters (one 64-byte block, reset by a memset each frame)
+// per-frame device counters (one 64-byte block, reset at the start of every frame by pack_frame_kernel)
 struct FrameCounters {
   int visible_count;
-  int pad0;
+  uint32_t frame;                 // frame stamp these counters belong to
   unsigned long long voxel_updates;
   unsigned long long triangles;
+  unsigned long long pad[5];
+};
+
+// Everything the host reads back after a frame, contiguous in HBM so that ONE small D2H copy fetches it
+// (the reference reads its heap counter with a 1x1 kernel and four memcpys, tsdf.cu:2318-2337).
+struct DeviceStatus {
+  FrameCounters c;
+  int map_error;                  // MapError bits, sticky
+  int heap_counter;               // number of allocated blocks (key_heap length)
+  int engine_error;               // sticky: 1 = triangle arena overflow
+  uint32_t overflow_frame;        // first frame whose marching cubes ran out of arena (0 = none); must follow engine_error
+  unsigned long long arena_top;   // triangles reserved in the arena
   unsigned long long pad[5];
 };
 
@@ -59,6 +74,7 @@ struct DeviceView {
   float* sdf;
   float* wgt;
   uchar4* rgb;
+  int* neg_count;                 // [pool_blocks] number of voxels with sdf < 0 per block, kept current by integrate_kernel
   int* visible;
   int list_cap;
   FrameCounters* counters;
@@ -69,11 +85,13 @@ struct DeviceView {
   unsigned long long* tri_offset; // [pool_blocks]
   int* tri_count;                 // [pool_blocks]
   int* engine_error;              // sticky: 1 = arena overflow this frame
+  uint32_t* overflow_frame;       // first frame that overflowed (0 = none)
 };
 
 // kernels (defined in the .cu files)
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st);
-void launch_pack_frame(const float* d_depth, const uint8_t* d_rgb, uint2* d_out, int npx, cudaStream_t st);
+void launch_pack_frame(const float* d_depth, const uint8_t* d_rgb, uint2* d_out, int npx, FrameCounters* reset_counters, uint32_t frame,
+                       cudaStream_t st);
 void launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* d_frame_px, bool color, const DeviceView& D, int num_sms,
                       cudaStream_t st);
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count,

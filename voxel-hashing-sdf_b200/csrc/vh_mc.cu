@@ -114,6 +114,118 @@ __device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int
   return cube;
 }
 
+// Mesh one block with the whole warp: stage the 9^3 tile, pass 1 lists candidate triangles, pass 2 writes the survivors.
+// B.nb_slot[0..8) holds the pool slots of the block and its seven upper neighbours (-1 = absent), `present` the same as bits.
+__device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D, const int slot, const unsigned present, const int (&halo)[7],
+                                          float* tile, unsigned short* wlist, const signed char* s_tri, const unsigned char* s_ntri,
+                                          const bool color, unsigned long long* __restrict__ out_offset, int* __restrict__ out_count,
+                                          const int lane, const uint32_t frame) {
+    // okbits bit q: every corner block a voxel with boundary mask q touches is present
+    bool okq = false;
+    if (lane < 8) {
+      okq = true;
+#pragma unroll
+      for (int m = 0; m < 8; m++) if ((m & lane) == m && !((present >> m) & 1u)) okq = false;
+    }
+    const unsigned okbits = __ballot_sync(0xffffffffu, okq) & 0xFFu;
+
+    // 9^3 tile: own 8^3 as four float4 per lane, then the 217 halo cells. While loading, note whether any cell is
+    // negative / non-negative: a tile of one sign class has cube index 0 or 255 everywhere and yields no triangle.
+    bool any_neg = false, any_pos = false;
+    {
+      const float* src = D.sdf + (size_t)slot * BLOCK_VOX;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int v = (j * 32 + lane) * 4;
+        const float4 q = *reinterpret_cast<const float4*>(src + v);
+        float* dst = tile + ((v >> 6) * TILE + ((v >> 3) & 7)) * TILE + (v & 7);
+        dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+        any_neg = any_neg || q.x < 0.0f || q.y < 0.0f || q.z < 0.0f || q.w < 0.0f;
+        any_pos = any_pos || !(q.x < 0.0f) || !(q.y < 0.0f) || !(q.z < 0.0f) || !(q.w < 0.0f);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 7; h++) {
+      const int d = halo[h];
+      if (d >= 0) {
+        const int s = B.nb_slot[(d >> 9) & 7];
+        const float v = s >= 0 ? D.sdf[(size_t)s * BLOCK_VOX + (d & 511)] : 0.0f;
+        tile[d >> 12] = v;
+        any_neg = any_neg || v < 0.0f;
+        any_pos = any_pos || !(v < 0.0f);
+      }
+    }
+    const bool mixed = __any_sync(0xffffffffu, any_neg) && __any_sync(0xffffffffu, any_pos);
+    if (!mixed) {
+      if (lane == 0) { out_offset[slot] = 0; out_count[slot] = 0; }
+      return 0;
+    }
+    __syncwarp();
+
+    // pass 1 (count): list the candidate triangles of the block as (tid << 3 | k) in the reference's slot order.
+    // Reference thread -> voxel mapping (tsdf.cu:903-906) for VPB = 8: tid = j*32 + lane -> x = tid >> 6,
+    // y = ((tid >> 3) - bz) & 7, z = tid & 7.
+    unsigned short* wl = wlist;
+    int nlist = 0;
+#pragma unroll 1
+    for (int j = 0; j < 16; j++) {
+      const int t = j * 32 + lane;
+      const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
+      const int need = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);
+      int nt = 0;
+      if ((okbits >> need) & 1u) nt = s_ntri[cube_index(tile, lx, ly, lz)];     // 0 for cube index 0 and 255
+      if (!__any_sync(0xffffffffu, nt > 0)) continue;
+      int incl = nt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      for (int k = 0; k < nt; k++) wl[nlist + incl - nt + k] = (unsigned short)((t << 3) | k);
+      nlist += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+
+    // one reservation per block for all candidates (the few degenerate ones leave unused arena slots behind the block's range)
+    unsigned long long base = 0;
+    bool fits = true;
+    if (nlist > 0) {
+      if (lane == 0) {
+        base = atomicAdd(D.arena_top, (unsigned long long)nlist);
+        if (base + (unsigned long long)nlist > D.arena_cap) { atomicOr(D.engine_error, 1); atomicCAS(D.overflow_frame, 0u, frame); fits = false; }
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      fits = __shfl_sync(0xffffffffu, fits, 0);
+    }
+
+    // pass 2 (emit): one candidate triangle per lane; survivors of the degenerate rule are written compactly, in order
+    int written = 0;
+    if (nlist > 0 && fits) {
+      for (int e0 = 0; e0 < nlist; e0 += 32) {
+        const int e = e0 + lane;
+        bool valid = false;
+        Vtx p0, p1, p2;
+        if (e < nlist) {
+          const int item = wl[e];
+          const int t = item >> 3, k = item & 7;
+          const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
+          const signed char* row = s_tri + cube_index(tile, lx, ly, lz) * 16 + 3 * k;
+          p0 = edge_vertex(B, D, lx, ly, lz, row[0], color);
+          p1 = edge_vertex(B, D, lx, ly, lz, row[1], color);
+          p2 = edge_vertex(B, D, lx, ly, lz, row[2], color);
+          valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(D.arena + base + (unsigned long long)(written + __popc(bal & ((1u << lane) - 1))));
+          dst[0] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), p0.c);
+          dst[1] = make_uint4(__float_as_uint(p1.x), __float_as_uint(p1.y), __float_as_uint(p1.z), p1.c);
+          dst[2] = make_uint4(__float_as_uint(p2.x), __float_as_uint(p2.y), __float_as_uint(p2.z), p2.c);
+        }
+        written += __popc(bal);
+      }
+    }
+    if (lane == 0) { out_offset[slot] = base; out_count[slot] = written; }
+    return written;
+}
+
 // One warp per voxel block, persistent over the list. Pass 1 finds which triangles survive, pass 2 writes them.
 __global__ void __launch_bounds__(MC_THREADS)
 marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int* __restrict__ list,
@@ -149,132 +261,57 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
     halo[h] = c < 217 ? ((((tx * TILE + ty) * TILE + tz) << 12) | (m << 9) | ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))) : -1;
   }
 
-  for (int i = gwarp; i < n; i += nwarps) {
-    const int entry = list[i];
-    const u64 key = D.map.keys[entry];
-    const int slot = D.map.slots[entry];
+  // The list is consumed four blocks at a time per warp: lane group g = lane >> 3 resolves block base+g and its seven
+  // +x/+y/+z neighbours (one lock-free probe per lane) and reads their negative-voxel counters (maintained by the
+  // integrate kernel). A block is meshed only if, among the blocks its 9^3 tile draws from, some voxel is negative and
+  // some is not — otherwise every cube index is 0 or 255 and the reference emits nothing for it either. In a room scan
+  // most of the working set is free space, so most blocks end here without their voxels being read.
+  for (int base = gwarp * 4; base < n; base += nwarps * 4) {
+    const int grp = lane >> 3, sub = lane & 7;
+    const int item = base + grp;
+    int entry = -1, slot = -1;
     McBlock B;
-    unpack_key(key, B.bx, B.by, B.bz);
-    B.tile = tile; B.nb_slot = s_nb[wid];
-
-    // the block and its seven +x/+y/+z neighbours: one lock-free probe per lane; a neighbour counts only if it is in the
-    // same list (this frame's working set, tsdf.cu:930,957-969) or, for full-map extraction, allocated at all
+    B.bx = B.by = B.bz = 0; B.tile = tile; B.nb_slot = s_nb[wid];
+    if (item < n) {
+      entry = list[item];
+      const u64 key = D.map.keys[entry];
+      slot = D.map.slots[entry];
+      unpack_key(key, B.bx, B.by, B.bz);
+    }
+    // a neighbour counts only if it is in the same list (this frame's working set, tsdf.cu:930,957-969) or, for
+    // full-map extraction, allocated at all
     int nb = -1;
-    if (lane == 0) nb = slot;
-    else if (lane < 8) {
-      const int nx = B.bx + (lane & 1), ny = B.by + ((lane >> 1) & 1), nz = B.bz + ((lane >> 2) & 1);
+    if (sub == 0) nb = slot;
+    else if (slot >= 0) {
+      const int nx = B.bx + (sub & 1), ny = B.by + ((sub >> 1) & 1), nz = B.bz + ((sub >> 2) & 1);
       if (key_in_range(nx, ny, nz)) {
         const int e = map_find(D.map, pack_key(nx, ny, nz));
         if (e >= 0 && (full_map || D.stamps[e] == frame)) nb = D.map.slots[e];
       }
     }
-    const unsigned present = __ballot_sync(0xffffffffu, nb >= 0) & 0xFFu;
-    if (lane < 8) s_nb[wid][lane] = nb;
-    __syncwarp();
-    // okbits bit q: every corner block a voxel with boundary mask q touches is present
-    bool okq = false;
-    if (lane < 8) {
-      okq = true;
-#pragma unroll
-      for (int m = 0; m < 8; m++) if ((m & lane) == m && !((present >> m) & 1u)) okq = false;
-    }
-    const unsigned okbits = __ballot_sync(0xffffffffu, okq) & 0xFFu;
+    const int nneg = nb >= 0 ? D.neg_count[nb] : 0;
+    const unsigned gsh = grp * 8;
+    const unsigned b_present = __ballot_sync(0xffffffffu, nb >= 0);
+    const unsigned b_neg = __ballot_sync(0xffffffffu, nb >= 0 && nneg > 0);
+    const unsigned b_pos = __ballot_sync(0xffffffffu, nb >= 0 && nneg < BLOCK_VOX);
+    const bool need = slot >= 0 && ((b_neg >> gsh) & 0xFFu) != 0 && ((b_pos >> gsh) & 0xFFu) != 0;
+    if (sub == 0 && slot >= 0 && !need) { out_offset[slot] = 0; out_count[slot] = 0; }
+    unsigned work = __ballot_sync(0xffffffffu, need && sub == 0);
 
-    // 9^3 tile: own 8^3 as four float4 per lane, then the 217 halo cells. While loading, note whether any cell is
-    // negative / non-negative: a tile of one sign class has cube index 0 or 255 everywhere and yields no triangle.
-    bool any_neg = false, any_pos = false;
-    if (slot >= 0) {
-      const float* src = D.sdf + (size_t)slot * BLOCK_VOX;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int v = (j * 32 + lane) * 4;
-        const float4 q = *reinterpret_cast<const float4*>(src + v);
-        float* dst = tile + ((v >> 6) * TILE + ((v >> 3) & 7)) * TILE + (v & 7);
-        dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
-        any_neg = any_neg || q.x < 0.0f || q.y < 0.0f || q.z < 0.0f || q.w < 0.0f;
-        any_pos = any_pos || !(q.x < 0.0f) || !(q.y < 0.0f) || !(q.z < 0.0f) || !(q.w < 0.0f);
-      }
+    while (work) {
+      const int src = __ffs(work) - 1;           // first lane of the group whose block is meshed now
+      work &= work - 1;
+      const int cur_slot = __shfl_sync(0xffffffffu, slot, src);
+      McBlock C;
+      C.bx = __shfl_sync(0xffffffffu, B.bx, src); C.by = __shfl_sync(0xffffffffu, B.by, src); C.bz = __shfl_sync(0xffffffffu, B.bz, src);
+      C.tile = tile; C.nb_slot = s_nb[wid];
+      const int my_nb = __shfl_sync(0xffffffffu, nb, src + (lane & 7));
+      const unsigned present = (b_present >> src) & 0xFFu;
+      __syncwarp();                              // previous block's readers of s_nb / tile / list are done
+      if (lane < 8) s_nb[wid][lane] = my_nb;
+      __syncwarp();
+      my_tris += (unsigned long long)mesh_block(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
     }
-#pragma unroll
-    for (int h = 0; h < 7; h++) {
-      const int d = halo[h];
-      if (d >= 0) {
-        const int s = s_nb[wid][(d >> 9) & 7];
-        const float v = s >= 0 ? D.sdf[(size_t)s * BLOCK_VOX + (d & 511)] : 0.0f;
-        tile[d >> 12] = v;
-        any_neg = any_neg || v < 0.0f;
-        any_pos = any_pos || !(v < 0.0f);
-      }
-    }
-    const bool mixed = __any_sync(0xffffffffu, any_neg) && __any_sync(0xffffffffu, any_pos);
-    if (!mixed || slot < 0) {
-      if (lane == 0 && slot >= 0) { out_offset[slot] = 0; out_count[slot] = 0; }
-      continue;
-    }
-    __syncwarp();
-
-    // pass 1 (count): list the candidate triangles of the block as (tid << 3 | k) in the reference's slot order.
-    // Reference thread -> voxel mapping (tsdf.cu:903-906) for VPB = 8: tid = j*32 + lane -> x = tid >> 6,
-    // y = ((tid >> 3) - bz) & 7, z = tid & 7.
-    unsigned short* wl = s_list[wid];
-    int nlist = 0;
-#pragma unroll 1
-    for (int j = 0; j < 16; j++) {
-      const int t = j * 32 + lane;
-      const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
-      const int need = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);
-      int nt = 0;
-      if ((okbits >> need) & 1u) nt = s_ntri[cube_index(tile, lx, ly, lz)];     // 0 for cube index 0 and 255
-      if (!__any_sync(0xffffffffu, nt > 0)) continue;
-      int incl = nt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-      for (int k = 0; k < nt; k++) wl[nlist + incl - nt + k] = (unsigned short)((t << 3) | k);
-      nlist += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    __syncwarp();
-
-    // one reservation per block for all candidates (the few degenerate ones leave unused arena slots behind the block's range)
-    unsigned long long base = 0;
-    bool fits = true;
-    if (nlist > 0) {
-      if (lane == 0) {
-        base = atomicAdd(D.arena_top, (unsigned long long)nlist);
-        if (base + (unsigned long long)nlist > D.arena_cap) { atomicOr(D.engine_error, 1); fits = false; }
-      }
-      base = __shfl_sync(0xffffffffu, base, 0);
-      fits = __shfl_sync(0xffffffffu, fits, 0);
-    }
-
-    // pass 2 (emit): one candidate triangle per lane; survivors of the degenerate rule are written compactly, in order
-    int written = 0;
-    if (nlist > 0 && fits) {
-      for (int e0 = 0; e0 < nlist; e0 += 32) {
-        const int e = e0 + lane;
-        bool valid = false;
-        Vtx p0, p1, p2;
-        if (e < nlist) {
-          const int item = wl[e];
-          const int t = item >> 3, k = item & 7;
-          const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
-          const signed char* row = s_tri + cube_index(tile, lx, ly, lz) * 16 + 3 * k;
-          p0 = edge_vertex(B, D, lx, ly, lz, row[0], color);
-          p1 = edge_vertex(B, D, lx, ly, lz, row[1], color);
-          p2 = edge_vertex(B, D, lx, ly, lz, row[2], color);
-          valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(D.arena + base + (unsigned long long)(written + __popc(bal & ((1u << lane) - 1))));
-          dst[0] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), p0.c);
-          dst[1] = make_uint4(__float_as_uint(p1.x), __float_as_uint(p1.y), __float_as_uint(p1.z), p1.c);
-          dst[2] = make_uint4(__float_as_uint(p2.x), __float_as_uint(p2.y), __float_as_uint(p2.z), p2.c);
-        }
-        written += __popc(bal);
-      }
-    }
-    if (lane == 0) { out_offset[slot] = base; out_count[slot] = written; my_tris += (unsigned long long)written; }
-    __syncwarp();   // tile and list are reused by the next block
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
