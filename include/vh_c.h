@@ -138,6 +138,28 @@ VH_API int vh_save_ply(vh_engine* e, const char* path, int mode);
 /* welded mesh: unique vertices (scaled by vox_size) + faces, as SavePLY would write them */
 VH_API int vh_weld_mesh(vh_engine* e, int mode, vh_vertex* verts, uint64_t vcap, uint64_t* nv, int32_t* faces, uint64_t fcap, uint64_t* nf);
 
+/* --- multi-GPU: one map sharded over several B200s, one engine per process and GPU ------------------------------
+ * (new: the reference is single-GPU.) Create every engine with the same vh_params except device and shard_rank
+ * (shard_count = number of GPUs); a block belongs to shard vh_owner_of_block(x, y, z, shard_count). Rank 0 obtains an
+ * NCCL id (vh_shard_unique_id) and passes it to the other processes by any means; every rank then calls
+ * vh_shard_connect (collective): NCCL communicator + CUDA-IPC mappings of the peers' tables and voxel planes, which the
+ * marching-cubes kernel reads directly over NVLink for block-border neighbours.
+ * vh_integrate_sharded (collective, same order on every rank): {pose, depth, rgb} are broadcast from rank 0 with NCCL on
+ * the engine's stream, every GPU allocates, integrates and meshes its own blocks. depth / rgb are read on rank 0 only;
+ * c2w may be NULL on the other ranks (they then take the broadcast pose at the price of a stream sync per frame).
+ * Asynchronous like vh_integrate_async: call vh_sync before reading results.
+ * vh_shard_gather_mesh (collective): the whole map's triangle soup on rank 0, merged in tsdf2mesh order, equal to the
+ * single-GPU result; other ranks get *n = 0. vh_shard_stats (collective): group-wide sums of the last frame's counters. */
+#define VH_NCCL_ID_BYTES 128
+VH_API int vh_owner_of_block(int x, int y, int z, int shard_count);
+VH_API int vh_shard_unique_id(uint8_t id[VH_NCCL_ID_BYTES]);
+VH_API int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]);
+VH_API int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w);
+VH_API int vh_shard_gather_mesh(vh_engine* e, int mode, vh_triangle* out, uint64_t cap, uint64_t* n);
+VH_API int vh_shard_stats(vh_engine* e, vh_stats* sum);
+/* host-only helper of the gather: merge per-shard block lists (each in mesh order) into the global mesh order */
+VH_API int vh_mesh_order_merge(int n_parts, const int32_t* const* keys_xyz, const int* nblocks, int blocks_per_chunk, int32_t* out_part, int32_t* out_index);
+
 /* pinned host memory helpers for callers that want DMA-able frame buffers */
 VH_API int vh_host_alloc(void** p, size_t bytes);
 VH_API int vh_host_free(void* p);

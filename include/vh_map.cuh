@@ -59,17 +59,18 @@ __host__ __device__ __forceinline__ uint32_t owner_of_key(u64 k, uint32_t shard_
 }
 
 #ifdef __CUDACC__
-// read-only lookup: entry index or -1
-__device__ __forceinline__ int map_find(const MapView& m, u64 key) {
-  uint32_t h = hash_key(key) & m.mask;
-  for (uint32_t probe = 0; probe <= m.mask; ++probe) {
-    const u64 cur = __ldcg(&m.keys[h]);
+// read-only lookup in a table given by its key array (own or a peer GPU's, mapped): entry index or -1
+__device__ __forceinline__ int map_find_in(const u64* __restrict__ keys, uint32_t mask, u64 key) {
+  uint32_t h = hash_key(key) & mask;
+  for (uint32_t probe = 0; probe <= mask; ++probe) {
+    const u64 cur = __ldcg(&keys[h]);
     if (cur == key) return (int)h;
     if (cur == KEY_EMPTY) return -1;
-    h = (h + 1) & m.mask;
+    h = (h + 1) & mask;
   }
   return -1;
 }
+__device__ __forceinline__ int map_find(const MapView& m, u64 key) { return map_find_in(m.keys, m.mask, key); }
 
 // insert-if-absent: entry index (>= 0) and whether THIS call claimed the entry; -1 when the table is full
 __device__ __forceinline__ int map_claim(const MapView& m, u64 key, bool& claimed) {

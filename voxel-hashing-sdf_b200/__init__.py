@@ -34,6 +34,8 @@ ABI_SYMBOLS = [
     "vh_extract_mesh", "vh_save_ply", "vh_weld_mesh", "vh_host_alloc", "vh_host_free",
     "vh_map_create", "vh_map_destroy", "vh_map_insert", "vh_map_find", "vh_map_erase", "vh_map_size", "vh_map_keys",
     "vh_map_get_view",
+    "vh_owner_of_block", "vh_shard_unique_id", "vh_shard_connect", "vh_integrate_sharded", "vh_shard_gather_mesh", "vh_shard_stats",
+    "vh_mesh_order_merge",
 ]
 
 
@@ -120,6 +122,13 @@ def load_library():
     L.vh_map_erase.argtypes = [vp, vp, ip, vp]
     L.vh_map_size.argtypes = [vp, C.POINTER(ip)]
     L.vh_map_keys.argtypes = [vp, vp, ip, C.POINTER(ip)]
+    L.vh_owner_of_block.argtypes = [ip, ip, ip, ip]
+    L.vh_shard_unique_id.argtypes = [vp]
+    L.vh_shard_connect.argtypes = [vp, vp]
+    L.vh_integrate_sharded.argtypes = [vp, vp, vp, vp]
+    L.vh_shard_gather_mesh.argtypes = [vp, ip, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.vh_shard_stats.argtypes = [vp, C.POINTER(VhStats)]
+    L.vh_mesh_order_merge.argtypes = [ip, vp, vp, ip, vp, vp]
     _lib = L
     return L
 
@@ -137,6 +146,22 @@ def default_params(**kw) -> VhParams:
             raise AttributeError(f"vh_params has no field {k}")
         setattr(p, k, v)
     return p
+
+
+def owner_of_block(x: int, y: int, z: int, shard_count: int) -> int:
+    """which shard of a multi-GPU map owns block (x, y, z)"""
+    return load_library().vh_owner_of_block(int(x), int(y), int(z), int(shard_count))
+
+
+def mesh_order_merge(parts, blocks_per_chunk: int = 8):
+    """parts: list of int32[n_i, 3] block-key arrays, each already in mesh order -> (part, index) arrays of the merged order"""
+    parts = [np.ascontiguousarray(p, np.int32).reshape(-1, 3) for p in parts]
+    n = sum(len(p) for p in parts)
+    ptrs = (C.c_void_p * len(parts))(*[p.ctypes.data for p in parts])
+    counts = np.array([len(p) for p in parts], np.int32)
+    op, oi = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+    _check(load_library().vh_mesh_order_merge(len(parts), C.cast(ptrs, C.c_void_p), counts.ctypes.data, blocks_per_chunk, op.ctypes.data, oi.ctypes.data))
+    return op[:n], oi[:n]
 
 
 def params_for_scene(scene, **kw) -> VhParams:
@@ -212,6 +237,42 @@ class TsdfEngine:
             rgb = np.ascontiguousarray(rgb, np.uint8)
             assert rgb.size == depth.size * 3
         return depth, rgb, c2w
+
+    # -- multi-GPU (one engine per process/GPU; see include/vh_c.h) --------------------------------
+    @staticmethod
+    def shard_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(load_library().vh_shard_unique_id(buf))
+        return bytes(buf)
+
+    def shard_connect(self, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self.L.vh_shard_connect(self.h, buf))
+
+    def integrate_sharded(self, depth, rgb, c2w):
+        """collective; depth/rgb may be None on ranks > 0"""
+        if depth is not None:
+            depth, rgb, c2w = self._host(depth, rgb, c2w)
+        elif c2w is not None:
+            c2w = np.ascontiguousarray(c2w, np.float32)
+        self._keep = (depth, rgb, c2w)
+        _check(self.L.vh_integrate_sharded(self.h, _ptr(depth), _ptr(rgb), _ptr(c2w)))
+
+    def shard_triangles(self, mode=VH_MESH_REF_PERSISTENT):
+        """collective; the merged soup on rank 0, empty arrays elsewhere"""
+        n = C.c_uint64()
+        _check(self.L.vh_shard_gather_mesh(self.h, mode, None, 0, C.byref(n)))
+        buf = np.zeros(max(n.value, 1), TRI_DTYPE)
+        _check(self.L.vh_shard_gather_mesh(self.h, mode, _ptr(buf), max(n.value, 1), C.byref(n)))
+        buf = buf[:n.value]
+        xyz = np.stack([buf["xyz0"], buf["xyz1"], buf["xyz2"]], 1) if n.value else np.zeros((0, 3, 3), np.float32)
+        rgb = np.stack([buf["rgb0"][:, :3], buf["rgb1"][:, :3], buf["rgb2"][:, :3]], 1) if n.value else np.zeros((0, 3, 3), np.uint8)
+        return xyz, rgb
+
+    def shard_stats(self) -> VhStats:
+        s = VhStats()
+        _check(self.L.vh_shard_stats(self.h, C.byref(s)))
+        return s
 
     # -- stages ---------------------------------------------------------------------------------
     def upload_frame(self, depth, rgb=None):

@@ -20,59 +20,17 @@
 #include <unordered_map>
 #include <vector>
 
-#include "vh_engine.h"
-
-using namespace vh;
+#include "vh_engine_host.h"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
   g_err = buf;
   return code;
 }
 extern "C" int vh_set_error_(int code, const char* msg) { g_err = msg ? msg : ""; return code; }
-#define CK(call)                                                                                          \
-  do {                                                                                                    \
-    cudaError_t _e = (call);                                                                              \
-    if (_e != cudaSuccess) return fail(VH_ERR_CUDA, "CUDA Error: %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #call); \
-  } while (0)
-
-struct vh_engine {
-  vh_params P;
-  StaticParams S;
-  FrameParams F;
-  DeviceView D;
-  int num_sms = 148;
-  uint32_t capacity = 0;
-  cudaStream_t stream = nullptr, upload = nullptr;
-  float* d_depth[2] = {nullptr, nullptr};
-  uint8_t* d_rgb[2] = {nullptr, nullptr};
-  uint2* d_px[2] = {nullptr, nullptr};     // packed {depth, rgb} records the integrate kernel reads
-  int px_ring = 0;
-  cudaEvent_t ev_uploaded[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-  bool buf_used[2] = {false, false};
-  int ring = 0;
-  const float* cur_depth = nullptr;     // device pointers the stage calls operate on
-  const uint8_t* cur_rgb = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  // pinned read-back block: counters of the last frame + flags
-  typedef DeviceStatus HostBlock;
-  HostBlock* h_block = nullptr;
-  DeviceStatus* d_status = nullptr;     // counters, error flags, heap counter, arena top: one block, one read-back copy
-  uint64_t frames = 0, updates_total = 0;
-  uint64_t max_tris_per_frame = 0, known_arena_top = 0;
-  int frames_in_flight = 0;
-  // full-map extraction scratch
-  int* d_full_list = nullptr; int* d_full_count = nullptr; unsigned long long* d_full_off = nullptr; int* d_full_cnt = nullptr;
-  u64* d_keys_tmp = nullptr; size_t keys_tmp_cap = 0;
-  // arena compaction: spare arena (ping-pong) and scan scratch
-  vh_triangle* arena_spare = nullptr;
-  unsigned long long *d_scan_in = nullptr, *d_scan_out = nullptr; void* d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
-  uint64_t compactions = 0;
-  std::mutex mtx;
-};
 
 // ---- frame constants on the host: getFrustumCenter / streamInCPU2GPU preamble (tsdf.cu:154-161, :197-206, :300-312)
 // compiled with -ffp-contract=off: plain float expressions in the reference's order
@@ -84,7 +42,7 @@ static void host_pixel_to_world(const vh_params& P, const float* c2w, int px, in
   out[2] = x * c2w[8] + y * c2w[9] + z * c2w[10] + c2w[11];
 }
 
-static void setup_frame(vh_engine* e, const float* c2w) {
+void setup_frame(vh_engine* e, const float* c2w) {
   FrameParams& F = e->F;
   const vh_params& P = e->P;
   memcpy(F.c2w, c2w, sizeof(F.c2w));
@@ -130,6 +88,7 @@ int vh_default_params(vh_params* p) {
 static int free_engine(vh_engine* e) {
   if (!e) return VH_OK;
   cudaSetDevice(e->P.device);
+  shard_release(e);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->upload) cudaStreamSynchronize(e->upload);
   DeviceView& D = e->D;
@@ -354,7 +313,7 @@ static int compact_arena(vh_engine* e, unsigned long long need) {
 }
 
 // ---- frame pipeline -----------------------------------------------------------------------------
-static int enqueue_stages(vh_engine* e, bool do_alloc) {
+int enqueue_stages(vh_engine* e, bool do_alloc) {
   DeviceView& D = e->D;
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
   // first kernel of the frame: packs {depth, rgb} records for integrate and resets the frame's counters
@@ -369,7 +328,7 @@ static int enqueue_stages(vh_engine* e, bool do_alloc) {
   return VH_OK;
 }
 
-static int enqueue_readback(vh_engine* e) {
+int enqueue_readback(vh_engine* e) {
   DeviceView& D = e->D;
   (void)D;
   CK(cudaMemcpyAsync(e->h_block, e->d_status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, e->stream));
@@ -377,7 +336,7 @@ static int enqueue_readback(vh_engine* e) {
 }
 
 // after a sync: fold the read-back block into host state, surface device-side errors, repair arena overflow
-static int finish_sync(vh_engine* e) {
+int finish_sync(vh_engine* e) {
   auto* hb = e->h_block;
   e->frames_in_flight = 0;
   e->known_arena_top = hb->arena_top;
@@ -410,7 +369,7 @@ static int finish_sync(vh_engine* e) {
 // Keep enough arena head-room for the frames that are in flight. The pinned status block is refreshed by every
 // frame's read-back copy, so it can be read without a sync: it tells which frame has completed, where the arena top
 // was then and how many triangles a frame produces.
-static int make_room(vh_engine* e) {
+int make_room(vh_engine* e) {
   if (!e->P.mc_per_frame) return VH_OK;
   const volatile DeviceStatus* hb = e->h_block;
   const uint64_t seen_frame = hb->c.frame, seen_top = hb->arena_top, seen_tris = hb->c.triangles;
@@ -724,15 +683,11 @@ int vh_voxel_checksum(vh_engine* e, double* sum_sdf, double* sum_w, uint64_t* n_
 }
 
 // ---- mesh assembly ------------------------------------------------------------------------------------
-struct MeshBlocks {
-  std::vector<u64> key; std::vector<unsigned long long> off; std::vector<int> cnt;
-  const vh_triangle* arena = nullptr; vh_triangle* tmp_arena = nullptr;
-};
 
 static inline int floor_div(int a, int b) { return (int)floorf((float)a / (float)b); }   // block2chunk, tsdf.cu:256-260
 
 // collect (key, offset, count) records, sorted in tsdf2mesh order: chunk x,y,z ascending, then block-in-chunk linear
-static int collect_blocks(vh_engine* e, int mode, MeshBlocks& mb) {
+int collect_blocks(vh_engine* e, int mode, MeshBlocks& mb) {
   DeviceView D = e->D;
   const int nb = e->P.pool_blocks;
   const unsigned long long* d_off = D.tri_offset; const int* d_cnt = D.tri_count;
@@ -804,6 +759,35 @@ static int collect_blocks(vh_engine* e, int mode, MeshBlocks& mb) {
   return VH_OK;
 }
 
+}  // extern "C"
+
+// copy the triangle ranges of mb's blocks, in mb's order, into one host array of `total` triangles
+int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out, unsigned long long total) {
+  const int n = (int)mb.key.size();
+  if (total == 0 || n == 0) return VH_OK;
+  std::vector<unsigned long long> dst((size_t)n);
+  unsigned long long acc = 0;
+  for (int i = 0; i < n; i++) { dst[i] = acc; acc += (unsigned long long)mb.cnt[i]; }
+  unsigned long long *d_src = nullptr, *d_dst = nullptr; int* d_cnt = nullptr; vh_triangle* d_out = nullptr;
+  cudaError_t ce = cudaMalloc((void**)&d_src, (size_t)n * sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_dst, (size_t)n * sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_cnt, (size_t)n * sizeof(int));
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_out, (size_t)total * sizeof(vh_triangle));
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_src, mb.off.data(), (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_dst, dst.data(), (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_cnt, mb.cnt.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    launch_gather_triangles(mb.arena, d_src, d_dst, d_cnt, n, d_out, e->stream);
+    ce = cudaStreamSynchronize(e->stream);
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, (size_t)total * sizeof(vh_triangle), cudaMemcpyDeviceToHost);
+  cudaFree(d_src); cudaFree(d_dst); cudaFree(d_cnt); cudaFree(d_out);
+  if (ce != cudaSuccess) return fail(VH_ERR_CUDA, "CUDA Error: %s while gathering triangles", cudaGetErrorString(ce));
+  return VH_OK;
+}
+
+extern "C" {
+
 static int extract_mesh_locked(vh_engine* e, int mode, std::vector<vh_triangle>* host_out, vh_triangle* out, uint64_t cap, uint64_t* n_out) {
   CK(cudaSetDevice(e->P.device));
   CK(cudaStreamSynchronize(e->stream));
@@ -812,34 +796,17 @@ static int extract_mesh_locked(vh_engine* e, int mode, std::vector<vh_triangle>*
   MeshBlocks mb;
   rc = collect_blocks(e, mode, mb);
   if (rc != VH_OK) { cudaFree(mb.tmp_arena); return rc; }
-  const int n = (int)mb.key.size();
-  std::vector<unsigned long long> dst((size_t)n);
   unsigned long long total = 0;
-  for (int i = 0; i < n; i++) { dst[i] = total; total += (unsigned long long)mb.cnt[i]; }
+  for (int c : mb.cnt) total += (unsigned long long)c;
   if (n_out) *n_out = total;
   if (host_out) { host_out->resize((size_t)total); out = host_out->data(); cap = total; }
-  if (out && total > 0 && cap >= total) {
-    unsigned long long *d_src = nullptr, *d_dst = nullptr; int* d_cnt = nullptr; vh_triangle* d_out = nullptr;
-    cudaError_t ce = cudaMalloc((void**)&d_src, (size_t)n * sizeof(unsigned long long));
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_dst, (size_t)n * sizeof(unsigned long long));
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_cnt, (size_t)n * sizeof(int));
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_out, (size_t)total * sizeof(vh_triangle));
-    if (ce == cudaSuccess) ce = cudaMemcpy(d_src, mb.off.data(), (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = cudaMemcpy(d_dst, dst.data(), (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = cudaMemcpy(d_cnt, mb.cnt.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) {
-      launch_gather_triangles(mb.arena, d_src, d_dst, d_cnt, n, d_out, e->stream);
-      ce = cudaStreamSynchronize(e->stream);
-    }
-    if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, (size_t)total * sizeof(vh_triangle), cudaMemcpyDeviceToHost);
-    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_cnt); cudaFree(d_out);
-    if (ce != cudaSuccess) { cudaFree(mb.tmp_arena); return fail(VH_ERR_CUDA, "CUDA Error: %s in vh_extract_mesh", cudaGetErrorString(ce)); }
-  } else if (out && total > cap) {
+  if (out && total > cap) {
     cudaFree(mb.tmp_arena);
     return fail(VH_ERR_INVALID, "output capacity %llu < %llu triangles", (unsigned long long)cap, total);
   }
+  if (out) rc = gather_block_triangles(e, mb, out, total);
   cudaFree(mb.tmp_arena);
-  return VH_OK;
+  return rc;
 }
 
 int vh_extract_mesh(vh_engine* e, int mode, vh_triangle* out, uint64_t cap, uint64_t* n) {

@@ -68,6 +68,15 @@ struct DeviceStatus {
   unsigned long long pad[5];
 };
 
+// What marching cubes needs from a shard of a multi-GPU map: its table and its voxel planes. Own pointers for the own
+// rank, CUDA-IPC mappings of the peers' allocations otherwise (read over NVLink by the kernel itself).
+constexpr int MAX_SHARDS = 8;
+struct PeerView {
+  const u64* keys; const int* slots; const uint32_t* stamps; const int* neg_count; const float* sdf; const uchar4* rgb;
+  uint32_t mask; uint32_t pad;
+};
+struct PeerTable { PeerView v[MAX_SHARDS]; };
+
 struct DeviceView {
   MapView map;
   uint32_t* stamps;
@@ -86,6 +95,7 @@ struct DeviceView {
   int* tri_count;                 // [pool_blocks]
   int* engine_error;              // sticky: 1 = arena overflow this frame
   uint32_t* overflow_frame;       // first frame that overflowed (0 = none)
+  const PeerTable* peers;         // multi-GPU: every shard's view (nullptr on a single GPU)
 };
 
 // kernels (defined in the .cu files)

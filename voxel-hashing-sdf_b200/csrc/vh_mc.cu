@@ -83,10 +83,12 @@ constexpr int TILE = 9, TILE_PAD = 736;   // 9^3 = 729 cells, padded
 struct McBlock {            // per-warp context of the block being meshed
   const float* tile;        // 9^3 sdf tile in shared memory
   const int* nb_slot;       // pool slots of the 8 corner blocks (bit0 +x, bit1 +y, bit2 +z), -1 = absent
+  const int* nb_owner;      // multi-GPU: shard that holds each corner block (its planes are read through D.peers)
   int bx, by, bz;
 };
 
 // vertex on cube edge e of the voxel at tile position (lx,ly,lz)
+template <bool SHARDED>
 __device__ __forceinline__ Vtx edge_vertex(const McBlock& B, const DeviceView& D, int lx, int ly, int lz, int e, bool color) {
   const int a = e < 8 ? e : e - 8;
   const int b = e < 4 ? ((e + 1) & 3) : (e < 8 ? 4 + ((e - 3) & 3) : e - 4);
@@ -97,9 +99,12 @@ __device__ __forceinline__ Vtx edge_vertex(const McBlock& B, const DeviceView& D
   pb.x = i2f(B.bx * VPB + qx); pb.y = i2f(B.by * VPB + qy); pb.z = i2f(B.bz * VPB + qz);
   pa.c = 0; pb.c = 0;
   if (color) {
-    const int sa = B.nb_slot[(ax >> 3) | ((ay >> 3) << 1) | ((az >> 3) << 2)], sb = B.nb_slot[(qx >> 3) | ((qy >> 3) << 1) | ((qz >> 3) << 2)];
-    const uchar4 ca = D.rgb[(size_t)sa * BLOCK_VOX + ((ax & 7) * 64 + (ay & 7) * 8 + (az & 7))];
-    const uchar4 cb = D.rgb[(size_t)sb * BLOCK_VOX + ((qx & 7) * 64 + (qy & 7) * 8 + (qz & 7))];
+    const int ma = (ax >> 3) | ((ay >> 3) << 1) | ((az >> 3) << 2), mb = (qx >> 3) | ((qy >> 3) << 1) | ((qz >> 3) << 2);
+    const int sa = B.nb_slot[ma], sb = B.nb_slot[mb];
+    const uchar4* rgb_a = SHARDED ? D.peers->v[B.nb_owner[ma]].rgb : D.rgb;
+    const uchar4* rgb_b = SHARDED ? D.peers->v[B.nb_owner[mb]].rgb : D.rgb;
+    const uchar4 ca = rgb_a[(size_t)sa * BLOCK_VOX + ((ax & 7) * 64 + (ay & 7) * 8 + (az & 7))];
+    const uchar4 cb = rgb_b[(size_t)sb * BLOCK_VOX + ((qx & 7) * 64 + (qy & 7) * 8 + (qz & 7))];
     pa.c = (uint32_t)ca.x | ((uint32_t)ca.y << 8) | ((uint32_t)ca.z << 16);
     pb.c = (uint32_t)cb.x | ((uint32_t)cb.y << 8) | ((uint32_t)cb.z << 16);
   }
@@ -116,6 +121,7 @@ __device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int
 
 // Mesh one block with the whole warp: stage the 9^3 tile, pass 1 lists candidate triangles, pass 2 writes the survivors.
 // B.nb_slot[0..8) holds the pool slots of the block and its seven upper neighbours (-1 = absent), `present` the same as bits.
+template <bool SHARDED>
 __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D, const int slot, const unsigned present, const int (&halo)[7],
                                           float* tile, unsigned short* wlist, const signed char* s_tri, const unsigned char* s_ntri,
                                           const bool color, unsigned long long* __restrict__ out_offset, int* __restrict__ out_count,
@@ -149,7 +155,8 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
       const int d = halo[h];
       if (d >= 0) {
         const int s = B.nb_slot[(d >> 9) & 7];
-        const float v = s >= 0 ? D.sdf[(size_t)s * BLOCK_VOX + (d & 511)] : 0.0f;
+        const float* plane = SHARDED ? D.peers->v[B.nb_owner[(d >> 9) & 7]].sdf : D.sdf;
+        const float v = s >= 0 ? plane[(size_t)s * BLOCK_VOX + (d & 511)] : 0.0f;
         tile[d >> 12] = v;
         any_neg = any_neg || v < 0.0f;
         any_pos = any_pos || !(v < 0.0f);
@@ -207,9 +214,9 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
           const int t = item >> 3, k = item & 7;
           const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
           const signed char* row = s_tri + cube_index(tile, lx, ly, lz) * 16 + 3 * k;
-          p0 = edge_vertex(B, D, lx, ly, lz, row[0], color);
-          p1 = edge_vertex(B, D, lx, ly, lz, row[1], color);
-          p2 = edge_vertex(B, D, lx, ly, lz, row[2], color);
+          p0 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[0], color);
+          p1 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[1], color);
+          p2 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[2], color);
           valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -227,12 +234,14 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
 }
 
 // One warp per voxel block, persistent over the list. Pass 1 finds which triangles survive, pass 2 writes them.
+template <bool SHARDED>
 __global__ void __launch_bounds__(MC_THREADS)
 marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int* __restrict__ list,
                       const int* __restrict__ list_count, const int full_map, unsigned long long* __restrict__ out_offset,
                       int* __restrict__ out_count) {
   __shared__ float s_tile[MC_WARPS][TILE_PAD];
   __shared__ int s_nb[MC_WARPS][8];
+  __shared__ int s_nbo[MC_WARPS][8];
   __shared__ unsigned short s_list[MC_WARPS][BLOCK_VOX * 5];   // candidate triangles of the block in flight
   __shared__ signed char s_tri[256 * 16];
   __shared__ unsigned char s_ntri[256];
@@ -271,7 +280,7 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
     const int item = base + grp;
     int entry = -1, slot = -1;
     McBlock B;
-    B.bx = B.by = B.bz = 0; B.tile = tile; B.nb_slot = s_nb[wid];
+    B.bx = B.by = B.bz = 0; B.tile = tile; B.nb_slot = s_nb[wid]; B.nb_owner = s_nbo[wid];
     if (item < n) {
       entry = list[item];
       const u64 key = D.map.keys[entry];
@@ -280,16 +289,24 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
     }
     // a neighbour counts only if it is in the same list (this frame's working set, tsdf.cu:930,957-969) or, for
     // full-map extraction, allocated at all
-    int nb = -1;
-    if (sub == 0) nb = slot;
+    int nb = -1, nb_owner = SHARDED ? (int)S.shard_rank : 0, nneg = 0;
+    if (sub == 0) { nb = slot; if (slot >= 0) nneg = D.neg_count[slot]; }
     else if (slot >= 0) {
       const int nx = B.bx + (sub & 1), ny = B.by + ((sub >> 1) & 1), nz = B.bz + ((sub >> 2) & 1);
       if (key_in_range(nx, ny, nz)) {
-        const int e = map_find(D.map, pack_key(nx, ny, nz));
-        if (e >= 0 && (full_map || D.stamps[e] == frame)) nb = D.map.slots[e];
+        const u64 nk = pack_key(nx, ny, nz);
+        if (SHARDED) {
+          // the neighbour lives on the GPU its key hashes to: probe that GPU's table and read its stamp / counter over NVLink
+          nb_owner = (int)owner_of_key(nk, S.shard_count);
+          const PeerView P = D.peers->v[nb_owner];
+          const int e = map_find_in(P.keys, P.mask, nk);
+          if (e >= 0 && (full_map || P.stamps[e] == frame)) { nb = P.slots[e]; if (nb >= 0) nneg = P.neg_count[nb]; }
+        } else {
+          const int e = map_find(D.map, nk);
+          if (e >= 0 && (full_map || D.stamps[e] == frame)) { nb = D.map.slots[e]; if (nb >= 0) nneg = D.neg_count[nb]; }
+        }
       }
     }
-    const int nneg = nb >= 0 ? D.neg_count[nb] : 0;
     const unsigned gsh = grp * 8;
     const unsigned b_present = __ballot_sync(0xffffffffu, nb >= 0);
     const unsigned b_neg = __ballot_sync(0xffffffffu, nb >= 0 && nneg > 0);
@@ -304,13 +321,14 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
       const int cur_slot = __shfl_sync(0xffffffffu, slot, src);
       McBlock C;
       C.bx = __shfl_sync(0xffffffffu, B.bx, src); C.by = __shfl_sync(0xffffffffu, B.by, src); C.bz = __shfl_sync(0xffffffffu, B.bz, src);
-      C.tile = tile; C.nb_slot = s_nb[wid];
+      C.tile = tile; C.nb_slot = s_nb[wid]; C.nb_owner = s_nbo[wid];
       const int my_nb = __shfl_sync(0xffffffffu, nb, src + (lane & 7));
+      const int my_nbo = __shfl_sync(0xffffffffu, nb_owner, src + (lane & 7));
       const unsigned present = (b_present >> src) & 0xFFu;
       __syncwarp();                              // previous block's readers of s_nb / tile / list are done
-      if (lane < 8) s_nb[wid][lane] = my_nb;
+      if (lane < 8) { s_nb[wid][lane] = my_nb; s_nbo[wid][lane] = my_nbo; }
       __syncwarp();
-      my_tris += (unsigned long long)mesh_block(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
+      my_tris += (unsigned long long)mesh_block<SHARDED>(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
     }
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
@@ -318,7 +336,10 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
 
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count, int full_map,
                            unsigned long long* out_offset, int* out_count, int num_sms, cudaStream_t st) {
-  marching_cubes_kernel<<<num_sms * 10, MC_THREADS, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count);
+  if (S.shard_count > 1 && D.peers)
+    marching_cubes_kernel<true><<<num_sms * 10, MC_THREADS, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count);
+  else
+    marching_cubes_kernel<false><<<num_sms * 10, MC_THREADS, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count);
 }
 
 }  // namespace vh

@@ -1,0 +1,408 @@
+// vh_shard.cu — one map sharded over several B200s (BASELINE config 4): one engine per process and GPU, block
+// ownership by a hash of the block coordinate, frames broadcast from rank 0 with NCCL, marching-cubes halos read
+// straight out of the owner GPU's memory over NVLink, meshes gathered on rank 0.
+//
+// The reference has no multi-GPU path (one global pair of tables, no cudaSetDevice); this is new.
+//   * vh_shard_connect: NCCL communicator (ncclCommInitRank) + an all-gather of CUDA-IPC handles of every rank's table
+//     and voxel planes. Each process maps its peers' allocations (cudaIpcOpenMemHandle) and uploads the PeerTable the
+//     sharded marching-cubes kernel walks: a neighbour block is looked up in the table of the GPU its key hashes to.
+//   * vh_integrate_sharded: ncclBroadcast of {pose, depth, rgb} from rank 0 on the engine's stream, then the normal
+//     frame pipeline with the owner filter in the allocation kernel; around marching cubes two stream-ordered NCCL
+//     barriers keep any GPU from meshing against voxels another GPU is still (or already again) integrating.
+//   * vh_shard_gather_mesh: every rank's ordered per-block triangle ranges go to rank 0 (ncclSend/ncclRecv), which
+//     merges them by the reference's mesh order (tsdf2mesh, tsdf.cu:1786-1806) — identical to the one-GPU soup.
+// NCCL is bound at run time (dlopen/dlsym) so that a process that already carries an NCCL (e.g. the one PyTorch
+// bundles) shares it and the single-GPU library has no NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "vh_engine_host.h"
+
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mtx;
+
+int load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mtx);
+  if (g_nccl.lib) return VH_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);     // whatever the process already carries
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(VH_ERR_INVALID, "NCCL not found (libnccl.so.2): %s", dlerror());
+#define VH_SYM(field, name)                                                                              \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));                               \
+  if (!g_nccl.field) return fail(VH_ERR_INVALID, "NCCL symbol %s missing", name)
+  VH_SYM(GetUniqueId, "ncclGetUniqueId"); VH_SYM(CommInitRank, "ncclCommInitRank"); VH_SYM(CommDestroy, "ncclCommDestroy");
+  VH_SYM(Broadcast, "ncclBroadcast"); VH_SYM(AllReduce, "ncclAllReduce"); VH_SYM(AllGather, "ncclAllGather");
+  VH_SYM(Send, "ncclSend"); VH_SYM(Recv, "ncclRecv"); VH_SYM(GroupStart, "ncclGroupStart"); VH_SYM(GroupEnd, "ncclGroupEnd");
+  VH_SYM(GetErrorString, "ncclGetErrorString");
+#undef VH_SYM
+  g_nccl.lib = h;
+  return VH_OK;
+}
+
+#define NK(call)                                                                                          \
+  do {                                                                                                    \
+    ncclResult_t _r = (call);                                                                             \
+    if (_r != ncclSuccess) return fail(VH_ERR_CUDA, "NCCL Error: %s at %s:%d (%s)", g_nccl.GetErrorString(_r), __FILE__, __LINE__, #call); \
+  } while (0)
+
+constexpr int N_SHARED = 6;     // keys, slots, stamps, neg_count, sdf, rgb
+struct ShardExport {
+  cudaIpcMemHandle_t h[N_SHARED];
+  uint32_t capacity; int pool_blocks; int has_rgb; int device;
+};
+
+}  // namespace
+
+struct vh_shard_state {
+  ncclComm_t comm = nullptr;
+  int rank = 0, count = 1;
+  void* mapped[MAX_SHARDS][N_SHARED] = {};
+  uint8_t* d_frame = nullptr;         // broadcast buffer: {c2w[16] f32 | depth f32[H*W] | rgb u8[H*W*3]}, double-buffered
+  size_t frame_bytes = 0;
+  uint8_t* h_frame = nullptr;         // pinned staging of the same layout (rank 0 packs the caller's buffers here)
+  int ring = 0;
+  cudaEvent_t consumed[2] = {nullptr, nullptr}; bool used[2] = {false, false};
+  int* d_token = nullptr;             // 1-int all-reduce = stream-ordered barrier across the GPUs
+  float* h_pose = nullptr;            // pinned: pose read back on ranks that were not given one
+};
+
+void shard_release(vh_engine* e) {
+  vh_shard_state* s = e->shard;
+  if (!s) return;
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (int r = 0; r < s->count; r++)
+    for (int k = 0; k < N_SHARED; k++)
+      if (r != s->rank && s->mapped[r][k]) cudaIpcCloseMemHandle(s->mapped[r][k]);
+  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  cudaFree(s->d_frame); cudaFree(s->d_token);
+  if (s->h_frame) cudaFreeHost(s->h_frame);
+  if (s->h_pose) cudaFreeHost(s->h_pose);
+  for (int i = 0; i < 2; i++) if (s->consumed[i]) cudaEventDestroy(s->consumed[i]);
+  cudaFree(e->d_peers); e->d_peers = nullptr; e->D.peers = nullptr;
+  delete s;
+  e->shard = nullptr;
+}
+
+// stream-ordered barrier: no GPU's later work on its engine stream starts before every GPU's earlier work is done
+static int shard_barrier(vh_engine* e) {
+  vh_shard_state* s = e->shard;
+  NK(g_nccl.AllReduce(s->d_token, s->d_token, 1, ncclInt, ncclSum, s->comm, e->stream));
+  return VH_OK;
+}
+
+extern "C" {
+
+// which shard owns a block (host-side twin of owner_of_key in include/vh_map.cuh)
+int vh_owner_of_block(int x, int y, int z, int shard_count) {
+  if (shard_count <= 0 || !key_in_range(x, y, z)) return -1;
+  return (int)owner_of_key(pack_key(x, y, z), (uint32_t)shard_count);
+}
+
+int vh_shard_unique_id(uint8_t id[VH_NCCL_ID_BYTES]) {
+  if (!id) return fail(VH_ERR_INVALID, "null argument");
+  int rc = load_nccl();
+  if (rc != VH_OK) return rc;
+  static_assert(VH_NCCL_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
+  ncclUniqueId u;
+  NK(g_nccl.GetUniqueId(&u));
+  memcpy(id, u.internal, VH_NCCL_ID_BYTES);
+  return VH_OK;
+}
+
+int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]) {
+  if (!e || !id) return fail(VH_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  if (e->shard) return fail(VH_ERR_INVALID, "engine already connected");
+  const int n = e->P.shard_count, r = e->P.shard_rank;
+  if (n < 2 || n > MAX_SHARDS) return fail(VH_ERR_INVALID, "shard_count must be 2..%d (got %d)", MAX_SHARDS, n);
+  int rc = load_nccl();
+  if (rc != VH_OK) return rc;
+  CK(cudaSetDevice(e->P.device));
+  vh_shard_state* s = new vh_shard_state;
+  s->rank = r; s->count = n;
+  e->shard = s;
+  ncclUniqueId u;
+  memcpy(u.internal, id, VH_NCCL_ID_BYTES);
+  NK(g_nccl.CommInitRank(&s->comm, n, u, r));
+  const size_t npx = (size_t)e->P.width * e->P.height;
+  s->frame_bytes = (64 + npx * 4 + npx * 3 + 255) / 256 * 256;
+  CK(cudaMalloc((void**)&s->d_frame, 2 * s->frame_bytes));
+  CK(cudaHostAlloc((void**)&s->h_frame, 2 * s->frame_bytes, cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&s->h_pose, 2 * 16 * sizeof(float), cudaHostAllocDefault));
+  CK(cudaMalloc((void**)&s->d_token, sizeof(int)));
+  CK(cudaMemset(s->d_token, 0, sizeof(int)));
+  for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
+
+  // exchange IPC handles of what a peer's marching cubes needs to read
+  ShardExport mine;
+  memset(&mine, 0, sizeof(mine));
+  void* ptrs[N_SHARED] = {e->D.map.keys, e->D.map.slots, e->D.stamps, e->D.neg_count, e->D.sdf, e->D.rgb};
+  for (int k = 0; k < N_SHARED; k++)
+    if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
+  mine.capacity = e->capacity; mine.pool_blocks = e->P.pool_blocks; mine.has_rgb = e->D.rgb ? 1 : 0; mine.device = e->P.device;
+  ShardExport* d_all = nullptr;
+  CK(cudaMalloc((void**)&d_all, sizeof(ShardExport) * n));
+  CK(cudaMemcpyAsync(d_all + r, &mine, sizeof(mine), cudaMemcpyHostToDevice, e->stream));
+  NK(g_nccl.AllGather(d_all + r, d_all, sizeof(ShardExport), ncclChar, s->comm, e->stream));
+  std::vector<ShardExport> all((size_t)n);
+  CK(cudaMemcpyAsync(all.data(), d_all, sizeof(ShardExport) * n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(d_all);
+
+  PeerTable pt;
+  memset(&pt, 0, sizeof(pt));
+  for (int q = 0; q < n; q++) {
+    if (all[q].capacity != e->capacity || all[q].has_rgb != mine.has_rgb)
+      return fail(VH_ERR_INVALID, "shard %d was created with different parameters (capacity %u vs %u)", q, all[q].capacity, e->capacity);
+    void* m[N_SHARED];
+    for (int k = 0; k < N_SHARED; k++) {
+      if (q == r) m[k] = ptrs[k];
+      else if (k == 5 && !all[q].has_rgb) m[k] = nullptr;
+      else {
+        cudaError_t ce = cudaIpcOpenMemHandle(&m[k], all[q].h[k], cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) return fail(VH_ERR_CUDA, "CUDA Error: cannot map shard %d's memory (%s): the GPUs need peer access (NVLink/NVSwitch)", q, cudaGetErrorString(ce));
+      }
+      s->mapped[q][k] = m[k];
+    }
+    PeerView& v = pt.v[q];
+    v.keys = (const u64*)m[0]; v.slots = (const int*)m[1]; v.stamps = (const uint32_t*)m[2]; v.neg_count = (const int*)m[3];
+    v.sdf = (const float*)m[4]; v.rgb = (const uchar4*)m[5]; v.mask = e->capacity - 1;
+  }
+  CK(cudaMalloc((void**)&e->d_peers, sizeof(PeerTable)));
+  CK(cudaMemcpy(e->d_peers, &pt, sizeof(pt), cudaMemcpyHostToDevice));
+  e->D.peers = e->d_peers;
+  rc = shard_barrier(e);
+  if (rc != VH_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return VH_OK;
+}
+
+// One frame on every GPU of the group (collective: every rank calls it, in the same order). depth / rgb are read on
+// rank 0 only (host pointers, like vh_integrate); c2w may be NULL on the other ranks, which then take the pose out of
+// the broadcast (one small D2H + stream sync per frame on those ranks; pass the pose everywhere to stay asynchronous).
+int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  vh_shard_state* s = e->shard;
+  if (!s) return fail(VH_ERR_INVALID, "vh_shard_connect has not been called");
+  if (s->rank == 0 && (!depth || !c2w)) return fail(VH_ERR_INVALID, "rank 0 must supply depth and pose");
+  CK(cudaSetDevice(e->P.device));
+  int rc = make_room(e);
+  if (rc != VH_OK) return rc;
+  const size_t npx = (size_t)e->P.width * e->P.height;
+  const int b = s->ring & 1; s->ring++;
+  uint8_t* dbuf = s->d_frame + (size_t)b * s->frame_bytes;
+  const bool with_rgb = e->S.use_color != 0;                      // group-wide: every rank was created with the same flag
+  const size_t bytes = 64 + npx * 4 + (with_rgb ? npx * 3 : 0);
+  CK(cudaEventRecord(e->ev[0], e->stream));
+  if (s->rank == 0) {
+    uint8_t* hbuf = s->h_frame + (size_t)b * s->frame_bytes;
+    if (s->used[b]) CK(cudaEventSynchronize(s->consumed[b]));    // the staging slot's previous upload has long finished; cheap
+    memcpy(hbuf, c2w, 64);
+    memcpy(hbuf + 64, depth, npx * 4);
+    if (with_rgb) { if (rgb) memcpy(hbuf + 64 + npx * 4, rgb, npx * 3); else memset(hbuf + 64 + npx * 4, 0, npx * 3); }
+    CK(cudaMemcpyAsync(dbuf, hbuf, bytes, cudaMemcpyHostToDevice, e->stream));
+  }
+  NK(g_nccl.Broadcast(dbuf, dbuf, bytes, ncclChar, 0, s->comm, e->stream));
+  CK(cudaEventRecord(e->ev[1], e->stream));
+  float pose[16];
+  if (c2w) memcpy(pose, c2w, sizeof(pose));
+  else {
+    CK(cudaMemcpyAsync(s->h_pose, dbuf, 64, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(pose, s->h_pose, sizeof(pose));
+  }
+  e->cur_depth = reinterpret_cast<const float*>(dbuf + 64);
+  e->cur_rgb = with_rgb ? dbuf + 64 + npx * 4 : nullptr;
+  setup_frame(e, pose);
+  // allocate (own blocks only) + integrate, then marching cubes between two barriers
+  DeviceView& D = e->D;
+  uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
+  launch_pack_frame(e->cur_depth, e->cur_rgb, px, (int)npx, D.counters, e->F.frame, e->stream);
+  launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
+  CK(cudaEventRecord(e->ev[2], e->stream));
+  launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
+  CK(cudaEventRecord(e->ev[3], e->stream));
+  if (e->P.mc_per_frame) {
+    rc = shard_barrier(e);                                        // every GPU has integrated frame f
+    if (rc != VH_OK) return rc;
+    launch_marching_cubes(e->S, e->F, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, e->num_sms, e->stream);
+    rc = shard_barrier(e);                                        // every GPU has meshed frame f: voxels may change again
+    if (rc != VH_OK) return rc;
+  }
+  CK(cudaEventRecord(e->ev[4], e->stream));
+  CK(cudaEventRecord(s->consumed[b], e->stream));
+  s->used[b] = true;
+  e->frames_in_flight++;
+  return enqueue_readback(e);
+}
+
+// group-wide sums of the last frame's counters (collective)
+int vh_shard_stats(vh_engine* e, vh_stats* sum) {
+  if (!e || !sum) return fail(VH_ERR_INVALID, "null argument");
+  vh_shard_state* s = e->shard;
+  if (!s) return fail(VH_ERR_INVALID, "vh_shard_connect has not been called");
+  vh_stats mine;
+  int rc = vh_get_stats(e, &mine);
+  if (rc != VH_OK) return rc;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  unsigned long long h[6] = {mine.visible_blocks, mine.allocated_blocks, mine.voxel_updates, mine.triangles, mine.arena_triangles, 0};
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(h)));
+  CK(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, e->stream));
+  NK(g_nccl.AllReduce(d, d, 6, ncclUint64, ncclSum, s->comm, e->stream));
+  CK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(d);
+  *sum = mine;
+  sum->visible_blocks = (uint32_t)h[0]; sum->allocated_blocks = (uint32_t)h[1]; sum->voxel_updates = h[2]; sum->triangles = h[3];
+  sum->arena_triangles = h[4];
+  return VH_OK;
+}
+
+// Host-side merge of per-shard block lists into the reference's mesh order. part p holds nblocks[p] blocks with
+// keys[p][3*i..] and counts[p][i] triangles, each part already in mesh order. out_part/out_index (length = total blocks)
+// receive, for every position of the merged order, which part and which block of that part comes next.
+int vh_mesh_order_merge(int n_parts, const int32_t* const* keys, const int* nblocks, int blocks_per_chunk, int32_t* out_part, int32_t* out_index) {
+  if (n_parts <= 0 || !keys || !nblocks || !out_part || !out_index || blocks_per_chunk <= 0) return fail(VH_ERR_INVALID, "invalid argument");
+  struct Head { int c[3]; int b[3]; };
+  auto head_of = [&](int p, int i) {
+    Head h;
+    for (int a = 0; a < 3; a++) { h.b[a] = keys[p][3 * (size_t)i + a]; h.c[a] = (int)floorf((float)h.b[a] / (float)blocks_per_chunk); }   // block2chunk, tsdf.cu:256-260
+    return h;
+  };
+  auto less = [](const Head& x, const Head& y) {
+    for (int a = 0; a < 3; a++) if (x.c[a] != y.c[a]) return x.c[a] < y.c[a];
+    for (int a = 0; a < 3; a++) if (x.b[a] != y.b[a]) return x.b[a] < y.b[a];
+    return false;
+  };
+  std::vector<int> pos((size_t)n_parts, 0);
+  size_t o = 0;
+  for (;;) {
+    int best = -1; Head bh{};
+    for (int p = 0; p < n_parts; p++) {
+      if (pos[p] >= nblocks[p]) continue;
+      const Head h = head_of(p, pos[p]);
+      if (best < 0 || less(h, bh)) { best = p; bh = h; }
+    }
+    if (best < 0) break;
+    out_part[o] = best; out_index[o] = pos[best]; pos[best]++; o++;
+  }
+  return VH_OK;
+}
+
+// The whole map's mesh on rank 0, in the reference's order (collective). Other ranks get *n = 0.
+int vh_shard_gather_mesh(vh_engine* e, int mode, vh_triangle* out, uint64_t cap, uint64_t* n_out) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  vh_shard_state* s = e->shard;
+  if (!s) return fail(VH_ERR_INVALID, "vh_shard_connect has not been called");
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  int rc = finish_sync(e);
+  if (rc != VH_OK) return rc;
+  if (mode == VH_MESH_FULL_MAP) { rc = shard_barrier(e); if (rc != VH_OK) return rc; CK(cudaStreamSynchronize(e->stream)); }   // peers' voxels are final
+  MeshBlocks mb;
+  rc = collect_blocks(e, mode, mb);
+  if (rc != VH_OK) { cudaFree(mb.tmp_arena); return rc; }
+  const int nb = (int)mb.key.size();
+  unsigned long long total = 0;
+  for (int c : mb.cnt) total += (unsigned long long)c;
+  std::vector<vh_triangle> tris((size_t)total);
+  rc = gather_block_triangles(e, mb, tris.data(), total);
+  cudaFree(mb.tmp_arena);
+  if (rc != VH_OK) return rc;
+  if (mode == VH_MESH_FULL_MAP) { rc = shard_barrier(e); if (rc != VH_OK) return rc; }   // nobody integrates while a peer still meshes
+
+  // sizes of every rank
+  unsigned long long mine[2] = {(unsigned long long)nb, total};
+  unsigned long long* d_sz = nullptr;
+  CK(cudaMalloc((void**)&d_sz, sizeof(mine) * s->count));
+  CK(cudaMemcpyAsync(d_sz + 2 * s->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, e->stream));
+  NK(g_nccl.AllGather(d_sz + 2 * s->rank, d_sz, 2, ncclUint64, s->comm, e->stream));
+  std::vector<unsigned long long> sz((size_t)2 * s->count);
+  CK(cudaMemcpyAsync(sz.data(), d_sz, sizeof(mine) * s->count, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(d_sz);
+
+  // per-block records (x, y, z, count) and triangles travel as bytes
+  std::vector<int32_t> rec((size_t)nb * 4);
+  for (int i = 0; i < nb; i++) { int x, y, z; unpack_key(mb.key[i], x, y, z); rec[4 * (size_t)i] = x; rec[4 * (size_t)i + 1] = y; rec[4 * (size_t)i + 2] = z; rec[4 * (size_t)i + 3] = mb.cnt[i]; }
+  if (s->rank != 0) {
+    uint8_t* d_buf = nullptr;
+    const size_t rb = rec.size() * sizeof(int32_t), tb = tris.size() * sizeof(vh_triangle);
+    CK(cudaMalloc((void**)&d_buf, rb + tb + 16));
+    if (rb) CK(cudaMemcpyAsync(d_buf, rec.data(), rb, cudaMemcpyHostToDevice, e->stream));
+    if (tb) CK(cudaMemcpyAsync(d_buf + rb, tris.data(), tb, cudaMemcpyHostToDevice, e->stream));
+    NK(g_nccl.Send(d_buf, rb + tb, ncclChar, 0, s->comm, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_buf);
+    if (n_out) *n_out = 0;
+    return VH_OK;
+  }
+  std::vector<std::vector<int32_t>> recs((size_t)s->count);
+  std::vector<std::vector<vh_triangle>> parts((size_t)s->count);
+  recs[0].swap(rec); parts[0].swap(tris);
+  unsigned long long grand = sz[1];
+  for (int q = 1; q < s->count; q++) {
+    const size_t rb = (size_t)sz[2 * q] * 4 * sizeof(int32_t), tb = (size_t)sz[2 * q + 1] * sizeof(vh_triangle);
+    grand += sz[2 * q + 1];
+    uint8_t* d_buf = nullptr;
+    CK(cudaMalloc((void**)&d_buf, rb + tb + 16));
+    NK(g_nccl.Recv(d_buf, rb + tb, ncclChar, q, s->comm, e->stream));
+    recs[q].resize((size_t)sz[2 * q] * 4); parts[q].resize((size_t)sz[2 * q + 1]);
+    if (rb) CK(cudaMemcpyAsync(recs[q].data(), d_buf, rb, cudaMemcpyDeviceToHost, e->stream));
+    if (tb) CK(cudaMemcpyAsync(parts[q].data(), d_buf + rb, tb, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_buf);
+  }
+  if (n_out) *n_out = grand;
+  if (!out) return VH_OK;
+  if (cap < grand) return fail(VH_ERR_INVALID, "output capacity %llu < %llu triangles", (unsigned long long)cap, grand);
+  // merge by mesh order
+  std::vector<std::vector<int32_t>> keys((size_t)s->count);
+  std::vector<std::vector<unsigned long long>> first((size_t)s->count);
+  std::vector<const int32_t*> kp((size_t)s->count);
+  std::vector<int> nbs((size_t)s->count);
+  size_t nblocks_all = 0;
+  for (int q = 0; q < s->count; q++) {
+    const size_t m = recs[q].size() / 4;
+    keys[q].resize(m * 3); first[q].resize(m);
+    unsigned long long acc = 0;
+    for (size_t i = 0; i < m; i++) { for (int a = 0; a < 3; a++) keys[q][3 * i + a] = recs[q][4 * i + a]; first[q][i] = acc; acc += (unsigned long long)recs[q][4 * i + 3]; }
+    kp[q] = keys[q].data(); nbs[q] = (int)m; nblocks_all += m;
+  }
+  std::vector<int32_t> op(nblocks_all), oi(nblocks_all);
+  rc = vh_mesh_order_merge(s->count, kp.data(), nbs.data(), e->P.blocks_per_chunk, op.data(), oi.data());
+  if (rc != VH_OK) return rc;
+  size_t w = 0;
+  for (size_t j = 0; j < nblocks_all; j++) {
+    const int q = op[j]; const size_t i = (size_t)oi[j];
+    const size_t cnt = (size_t)recs[q][4 * i + 3];
+    if (cnt) memcpy(out + w, parts[q].data() + first[q][i], cnt * sizeof(vh_triangle));
+    w += cnt;
+  }
+  return VH_OK;
+}
+
+}  // extern "C"
