@@ -66,6 +66,8 @@ typedef struct vh_params {
   int mc_per_frame;             /* 1: working-set marching cubes every frame (tsdf.cu:1544); 0: on demand      */
   int device;                   /* CUDA device ordinal                                                         */
   int shard_rank, shard_count;  /* multi-GPU: this engine owns blocks with owner(key) == shard_rank            */
+  int shard_group;              /* ownership granularity, blocks per axis; 0 = blocks_per_chunk (8): neighbours
+                                   mostly share an owner, so few marching-cubes halo reads cross NVLink          */
   int depth_tile_smem;          /* 1: stage per-block depth tiles through TMA/shared memory in integrate       */
   uint64_t tri_arena_bytes;     /* triangle arena size (grows on demand); 0 = default 1 GiB. With mc_per_frame a
                                    second arena of the same size is held as the compaction target                */
@@ -140,7 +142,8 @@ VH_API int vh_weld_mesh(vh_engine* e, int mode, vh_vertex* verts, uint64_t vcap,
 
 /* --- multi-GPU: one map sharded over several B200s, one engine per process and GPU ------------------------------
  * (new: the reference is single-GPU.) Create every engine with the same vh_params except device and shard_rank
- * (shard_count = number of GPUs); a block belongs to shard vh_owner_of_block(x, y, z, shard_count). Rank 0 obtains an
+ * (shard_count = number of GPUs); a block belongs to shard
+ * vh_owner_of_block(x, y, z, shard_count, shard_group): ownership is hashed per cube of shard_group^3 blocks. Rank 0 obtains an
  * NCCL id (vh_shard_unique_id) and passes it to the other processes by any means; every rank then calls
  * vh_shard_connect (collective): NCCL communicator + CUDA-IPC mappings of the peers' tables and voxel planes, which the
  * marching-cubes kernel reads directly over NVLink for block-border neighbours.
@@ -151,7 +154,7 @@ VH_API int vh_weld_mesh(vh_engine* e, int mode, vh_vertex* verts, uint64_t vcap,
  * vh_shard_gather_mesh (collective): the whole map's triangle soup on rank 0, merged in tsdf2mesh order, equal to the
  * single-GPU result; other ranks get *n = 0. vh_shard_stats (collective): group-wide sums of the last frame's counters. */
 #define VH_NCCL_ID_BYTES 128
-VH_API int vh_owner_of_block(int x, int y, int z, int shard_count);
+VH_API int vh_owner_of_block(int x, int y, int z, int shard_count, int shard_group);
 VH_API int vh_shard_unique_id(uint8_t id[VH_NCCL_ID_BYTES]);
 VH_API int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]);
 VH_API int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w);

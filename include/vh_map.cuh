@@ -57,6 +57,14 @@ __host__ __device__ __forceinline__ uint32_t owner_of_key(u64 k, uint32_t shard_
   k *= 0x9E3779B97F4A7C15ull; k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull; k ^= k >> 32;
   return (uint32_t)(k % shard_count);
 }
+// Ownership is decided per cube of `group` blocks per axis (group = 1: per block; group = 8: per reference chunk). A
+// block and its +x/+y/+z neighbours then share an owner unless they straddle a cube face: with group = 8 four out of
+// five marching-cubes neighbour look-ups stay on the local GPU.
+__host__ __device__ __forceinline__ int floor_div_int(int a, int b) { const int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+__host__ __device__ __forceinline__ uint32_t owner_of_block(int x, int y, int z, uint32_t shard_count, int group) {
+  if (group > 1) { x = floor_div_int(x, group); y = floor_div_int(y, group); z = floor_div_int(z, group); }
+  return owner_of_key(pack_key(x, y, z), shard_count);
+}
 
 #ifdef __CUDACC__
 // read-only lookup in a table given by its key array (own or a peer GPU's, mapped): entry index or -1

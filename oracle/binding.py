@@ -201,6 +201,11 @@ def ref_emu_available(vpb: int) -> bool:
     return os.path.exists(ref_emu_path(vpb))
 
 
+def ref_cuda_path(variant: str) -> str:
+    """the reference's own tsdf.cu built by oracle/build_ref_cuda.sh as a real CUDA library (baseline timing on the GPU box)"""
+    return os.path.join(HERE, "_ref", f"libref_cuda_vpb{variant}.so")
+
+
 class RefEmu:
     """The reference's own GpuTsdfGenerator (src/tsdf.cu) running sequentially on the CPU.
 
@@ -209,8 +214,8 @@ class RefEmu:
     reference's: 8 blocks per chunk, DDA stride 10, 100 ray steps, +-64 chunks, min depth 0.1.
     """
 
-    def __init__(self, scene, vpb: int, vox_size: float, trunc: float, max_depth: float = 10.0):
-        L = C.CDLL(ref_emu_path(vpb))
+    def __init__(self, scene, vpb: int, vox_size: float, trunc: float, max_depth: float = 10.0, lib_path: str = None):
+        L = C.CDLL(lib_path or ref_emu_path(vpb))
         vp = C.c_void_p
         L.ref_create.restype = vp
         L.ref_create.argtypes = [C.c_int] * 2 + [C.c_float] * 7
@@ -282,3 +287,17 @@ class RefEmu:
 
     def save_ply(self, path: str):
         self.L.ref_save_ply(self.h, path.encode())
+
+
+class RefCuda(RefEmu):
+    """The reference's own CUDA build (oracle/build_ref_cuda.sh) on a real GPU: processFrame unchanged, results read out of
+    its host chunk store. The per-frame key hook of the emulated build does not exist here (key_heap lives on the device)."""
+
+    def __init__(self, scene, variant: str, vox_size: float, trunc: float, max_depth: float = 10.0):
+        super().__init__(scene, 8 if variant.startswith("8") else 5, vox_size, trunc, max_depth, lib_path=ref_cuda_path(variant))
+
+    def visible_keys(self):
+        raise NotImplementedError("the CUDA build keeps key_heap on the device")
+
+    def triangle_count(self):
+        return int(self.L.ref_triangles(self.h, None, None, 0))

@@ -25,11 +25,18 @@ def main():
     vh = importlib.import_module("voxel-hashing-sdf_b200")
     rng = np.random.RandomState(7)                                   # same list on every rank
     keys = np.unique(rng.randint(-300, 300, size=(20000, 3)).astype(np.int32), axis=0)
-    owner = np.array([vh.owner_of_block(*k, world) for k in keys])
+    owner = np.array([vh.owner_of_block(*k, world, 1) for k in keys])
     assert owner.min() >= 0 and owner.max() < world
     mine = mesh_order(keys[owner == rank])
-    # every rank owns a fair share, and ownership does not follow the coordinate order (neighbours spread over the shards)
+    # every rank owns a fair share
     assert abs(len(mine) - len(keys) / world) < 0.05 * len(keys)
+    # default granularity: one owner per 8^3-block cube (the reference's chunk), so most +x/+y/+z neighbours share it
+    own8 = np.array([vh.owner_of_block(*k, world) for k in keys])
+    cube = np.floor(keys / 8.0).astype(np.int64)
+    first = {}
+    for c, o in zip(map(tuple, cube), own8):
+        assert first.setdefault(c, o) == o, "blocks of one cube must share an owner"
+    assert abs((own8 == rank).mean() - 1.0 / world) < 0.1
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     total = sum(len(g) for g in gathered)
@@ -40,7 +47,7 @@ def main():
         merged = np.stack([gathered[p][i] for p, i in zip(part, idx)])
         assert np.array_equal(merged, mesh_order(keys)), "merge of the shards' lists must equal the global mesh order"
         # out-of-range coordinates have no owner
-        assert vh.owner_of_block(1 << 21, 0, 0, world) == -1
+        assert vh.owner_of_block(1 << 21, 0, 0, world, 1) == -1
         print("MULTI_HOST_OK", len(keys), [len(g) for g in gathered], flush=True)
     dist.barrier()
     dist.destroy_process_group()

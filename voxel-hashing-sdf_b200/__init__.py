@@ -55,7 +55,7 @@ class VhParams(C.Structure):
                 ("chunk_radius", C.c_float), ("max_chunk_num", C.c_int),
                 ("num_buckets", C.c_int), ("entries_per_bucket", C.c_int), ("pool_blocks", C.c_int),
                 ("use_color", C.c_int), ("mc_per_frame", C.c_int), ("device", C.c_int),
-                ("shard_rank", C.c_int), ("shard_count", C.c_int), ("depth_tile_smem", C.c_int),
+                ("shard_rank", C.c_int), ("shard_count", C.c_int), ("shard_group", C.c_int), ("depth_tile_smem", C.c_int),
                 ("tri_arena_bytes", C.c_uint64)]
 
 
@@ -122,7 +122,7 @@ def load_library():
     L.vh_map_erase.argtypes = [vp, vp, ip, vp]
     L.vh_map_size.argtypes = [vp, C.POINTER(ip)]
     L.vh_map_keys.argtypes = [vp, vp, ip, C.POINTER(ip)]
-    L.vh_owner_of_block.argtypes = [ip, ip, ip, ip]
+    L.vh_owner_of_block.argtypes = [ip, ip, ip, ip, ip]
     L.vh_shard_unique_id.argtypes = [vp]
     L.vh_shard_connect.argtypes = [vp, vp]
     L.vh_integrate_sharded.argtypes = [vp, vp, vp, vp]
@@ -148,9 +148,9 @@ def default_params(**kw) -> VhParams:
     return p
 
 
-def owner_of_block(x: int, y: int, z: int, shard_count: int) -> int:
-    """which shard of a multi-GPU map owns block (x, y, z)"""
-    return load_library().vh_owner_of_block(int(x), int(y), int(z), int(shard_count))
+def owner_of_block(x: int, y: int, z: int, shard_count: int, shard_group: int = 8) -> int:
+    """which shard of a multi-GPU map owns block (x, y, z); ownership is hashed per cube of shard_group^3 blocks"""
+    return load_library().vh_owner_of_block(int(x), int(y), int(z), int(shard_count), int(shard_group))
 
 
 def mesh_order_merge(parts, blocks_per_chunk: int = 8):
@@ -251,7 +251,7 @@ class TsdfEngine:
 
     def integrate_sharded(self, depth, rgb, c2w):
         """collective; depth/rgb may be None on ranks > 0"""
-        if depth is not None:
+        if depth is not None and not isinstance(depth, int):
             depth, rgb, c2w = self._host(depth, rgb, c2w)
         elif c2w is not None:
             c2w = np.ascontiguousarray(c2w, np.float32)

@@ -128,7 +128,7 @@ alloc_visible_kernel(const StaticParams S, const FrameParams F, const float* __r
       unpack_key(key, bx, by, bz);
       bool ok = chunk_is_candidate(S, F, block_to_chunk(bx, bpc), block_to_chunk(by, bpc), block_to_chunk(bz, bpc));   // tsdf.cu:2164
       if (ok) ok = block_in_frustum(S, F, bx, by, bz);                                                                  // tsdf.cu:2165
-      if (ok && S.shard_count > 1) ok = owner_of_key(key, S.shard_count) == S.shard_rank;
+      if (ok && S.shard_count > 1) ok = owner_of_block(bx, by, bz, S.shard_count, S.shard_group) == S.shard_rank;
       if (!ok) key = KEY_EMPTY;
     }
     if (__ballot_sync(0xffffffffu, key != KEY_EMPTY) == 0) continue;

@@ -79,7 +79,7 @@ int vh_default_params(vh_params* p) {
   p->num_buckets = 1 << 20; p->entries_per_bucket = 4;
   p->pool_blocks = 1 << 20;
   p->use_color = 1; p->mc_per_frame = 1;
-  p->device = 0; p->shard_rank = 0; p->shard_count = 1;
+  p->device = 0; p->shard_rank = 0; p->shard_count = 1; p->shard_group = 0;
   p->depth_tile_smem = 1;
   p->tri_arena_bytes = 0;
   return VH_OK;
@@ -171,6 +171,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   S.nry = std::min(gy, (p->height + p->dda_stride - 1) / p->dda_stride);
   S.use_color = p->use_color ? 1 : 0;
   S.shard_rank = (uint32_t)p->shard_rank; S.shard_count = (uint32_t)p->shard_count;
+  S.shard_group = p->shard_group > 0 ? p->shard_group : p->blocks_per_chunk;
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '2' && v[0] <= '4') ? v[0] - '0' : 4; }   // tuning knobs
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
@@ -343,6 +344,7 @@ int finish_sync(vh_engine* e) {
   e->max_tris_per_frame = std::max<uint64_t>(e->max_tris_per_frame, hb->c.triangles);
   if (hb->map_error & MAP_TABLE_FULL) return fail(VH_ERR_TABLE_FULL, "hash table full (%u entries): raise num_buckets/entries_per_bucket", e->capacity);
   if (hb->map_error & MAP_POOL_FULL) return fail(VH_ERR_POOL_FULL, "out of block memory: pool of %d voxel blocks exhausted, raise pool_blocks", e->P.pool_blocks);
+  if (hb->engine_error & 8) return fail(VH_ERR_CUDA, "CUDA Error: a peer GPU of the sharded map did not reach a frame barrier within 4 s");
   if (hb->engine_error & 2) return fail(VH_ERR_CUDA, "CUDA Error: integrate met a value outside the validated range of its division sequence");
   if (hb->engine_error & 1) {
     // marching cubes ran out of arena. Compact/grow; if only the last frame was hit, redo it (it only reads voxels + stamps).

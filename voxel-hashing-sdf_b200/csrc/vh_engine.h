@@ -33,6 +33,7 @@ struct StaticParams {
   int nrx, nry;                   // sampled rays per row / column (reference launch shape, tsdf.cu:2263-2264)
   int use_color;
   uint32_t shard_rank, shard_count;
+  int shard_group;                // ownership granularity in blocks per axis
   float round_eps;                // distance from a .5 pixel tie below which integrate re-projects with IEEE divisions
   int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
   int integrate_two_steps;        // tuning: 1 = gate/load/update two steps of a block together, 0 = one step at a time (default)

@@ -297,7 +297,7 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
         const u64 nk = pack_key(nx, ny, nz);
         if (SHARDED) {
           // the neighbour lives on the GPU its key hashes to: probe that GPU's table and read its stamp / counter over NVLink
-          nb_owner = (int)owner_of_key(nk, S.shard_count);
+          nb_owner = (int)owner_of_block(nx, ny, nz, S.shard_count, S.shard_group);
           const PeerView P = D.peers->v[nb_owner];
           const int e = map_find_in(P.keys, P.mask, nk);
           if (e >= 0 && (full_map || P.stamps[e] == frame)) { nb = P.slots[e]; if (nb >= 0) nneg = P.neg_count[nb]; }
