@@ -17,4 +17,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:marc
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_mc_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:alloc_visible_kernel -s 120 -c 2 -f -o $OUT/prof_alloc_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_alloc_$TAG.log 2>&1
-tail -3 $OUT/pytest_gpu_$TAG.log $OUT/smoke_$TAG.log $OUT/bench_$TAG.log
+tail -n 3 $OUT/pytest_gpu_$TAG.log; tail -n 2 $OUT/smoke_$TAG.log; tail -c 600 $OUT/bench_$TAG.log

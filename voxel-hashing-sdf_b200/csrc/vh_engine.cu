@@ -93,7 +93,7 @@ static int free_engine(vh_engine* e) {
   if (e->upload) cudaStreamSynchronize(e->upload);
   DeviceView& D = e->D;
   cudaFree(D.map.keys); cudaFree(D.map.slots); cudaFree(D.map.free_list); cudaFree(D.map.free_top); cudaFree(D.map.key_heap);
-  cudaFree(e->d_status); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.neg_count); cudaFree(D.visible);
+  cudaFree(e->d_status); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.neg_count); cudaFree(D.mc_queue); cudaFree(D.mc_ctl); cudaFree(D.visible);
   cudaFree(D.arena); cudaFree(e->arena_spare); cudaFree(e->d_scan_in); cudaFree(e->d_scan_out); cudaFree(e->d_scan_tmp);
   cudaFree(D.tri_offset); cudaFree(D.tri_count);
   cudaFree(e->d_full_list); cudaFree(e->d_full_count); cudaFree(e->d_full_off); cudaFree(e->d_full_cnt); cudaFree(e->d_keys_tmp);
@@ -126,6 +126,7 @@ static int reset_map(vh_engine* e) {
   CK(cudaMemsetAsync(D.wgt, 0, (size_t)nb * BLOCK_VOX * sizeof(float), e->stream));
   if (D.rgb) CK(cudaMemsetAsync(D.rgb, 0, (size_t)nb * BLOCK_VOX * sizeof(uchar4), e->stream));
   CK(cudaMemsetAsync(D.neg_count, 0, (size_t)nb * sizeof(int), e->stream));
+  CK(cudaMemsetAsync(D.mc_ctl, 0, 2 * sizeof(McQueueCtl), e->stream));
   CK(cudaMemsetAsync(D.tri_offset, 0, (size_t)nb * sizeof(unsigned long long), e->stream));
   CK(cudaMemsetAsync(D.tri_count, 0, (size_t)nb * sizeof(int), e->stream));
   CK(cudaMemsetAsync(e->d_status, 0, sizeof(DeviceStatus), e->stream));
@@ -207,6 +208,8 @@ int vh_create(const vh_params* p, vh_engine** out) {
   ALLOC(D.wgt, nb * BLOCK_VOX * sizeof(float));
   if (S.use_color) ALLOC(D.rgb, nb * BLOCK_VOX * sizeof(uchar4));
   ALLOC(D.neg_count, nb * sizeof(int));
+  ALLOC(D.mc_queue, (size_t)D.list_cap * sizeof(McWork));
+  ALLOC(D.mc_ctl, 2 * sizeof(McQueueCtl));
   ALLOC(D.visible, (size_t)D.list_cap * sizeof(int));
   ALLOC(D.arena, D.arena_cap * sizeof(vh_triangle));
   if (p->mc_per_frame) ALLOC(e->arena_spare, D.arena_cap * sizeof(vh_triangle));      // compaction target; the two swap roles
@@ -221,6 +224,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
 #undef ALLOC
   D.map.mask = e->capacity - 1;
   D.map.num_blocks = p->pool_blocks;
+  D.mc_parity = &e->mc_parity;
   D.counters = &e->d_status->c;
   D.map.error_flag = &e->d_status->map_error;
   D.engine_error = &e->d_status->engine_error;

@@ -78,6 +78,16 @@ struct PeerView {
 };
 struct PeerTable { PeerView v[MAX_SHARDS]; };
 
+// marching-cubes work queue: blocks that passed the neighbourhood sign filter
+struct McWork {
+  int bx, by, bz, slot;
+  int nb[8];                      // pool slots of the 8 corner blocks (bit0 +x, bit1 +y, bit2 +z), -1 = absent
+  unsigned char owner[8];         // multi-GPU: shard holding each corner block
+  unsigned present;               // nb[i] >= 0 as bits
+  unsigned pad;
+};
+struct McQueueCtl { int count; int head; };
+
 struct DeviceView {
   MapView map;
   uint32_t* stamps;
@@ -97,6 +107,9 @@ struct DeviceView {
   int* engine_error;              // sticky: 1 = arena overflow this frame
   uint32_t* overflow_frame;       // first frame that overflowed (0 = none)
   const PeerTable* peers;         // multi-GPU: every shard's view (nullptr on a single GPU)
+  McWork* mc_queue;               // [list_cap] marching-cubes work queue
+  McQueueCtl* mc_ctl;             // [2] queue control, alternating per launch
+  int* mc_parity;                 // host-side toggle selecting the control slot of the next launch
 };
 
 // kernels (defined in the .cu files)

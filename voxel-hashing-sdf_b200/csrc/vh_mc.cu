@@ -33,6 +33,8 @@ __constant__ signed char c_tri[256][16];
 __constant__ unsigned char c_ntri[256];
 __constant__ unsigned short c_edge_mask[256];
 
+static uint4* g_tables_dev[16] = {};          // per device: expanded case tables in global memory (mesh kernel copies them to shared)
+
 void upload_mc_tables() {
   for (int k = 0; k < 8; k++)
     if (corner_ox(k) != VH_MC_CORNER_OFFSET[k][0] || corner_oy(k) != VH_MC_CORNER_OFFSET[k][1] || corner_oz(k) != VH_MC_CORNER_OFFSET[k][2]) abort();
@@ -45,6 +47,13 @@ void upload_mc_tables() {
   cudaMemcpyToSymbol(c_tri, tri, sizeof(tri));
   cudaMemcpyToSymbol(c_ntri, ntri, sizeof(ntri));
   cudaMemcpyToSymbol(c_edge_mask, em, sizeof(em));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_tables_dev[dev & 15]) {
+    cudaMalloc((void**)&g_tables_dev[dev & 15], sizeof(tri) + sizeof(ntri));
+    cudaMemcpy(g_tables_dev[dev & 15], tri, sizeof(tri), cudaMemcpyHostToDevice);
+    cudaMemcpy(reinterpret_cast<char*>(g_tables_dev[dev & 15]) + sizeof(tri), ntri, sizeof(ntri), cudaMemcpyHostToDevice);
+  }
 }
 
 struct Vtx { float x, y, z; uint32_t c; };   // c = r | g<<8 | b<<16
@@ -233,66 +242,38 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
     return written;
 }
 
-// One warp per voxel block, persistent over the list. Pass 1 finds which triangles survive, pass 2 writes them.
+// ---- stage 1: filter ------------------------------------------------------------------------------------------------
+// The list is consumed four blocks at a time per warp: lane group g = lane >> 3 resolves block base+g and its seven
+// +x/+y/+z neighbours (one lock-free probe per lane) and reads their negative-voxel counters (maintained by the
+// integrate kernel). A block goes on to meshing only if, among the blocks its 9^3 tile draws from, some voxel is
+// negative and some is not — otherwise every cube index is 0 or 255 and the reference emits nothing for it either. In a
+// room scan most of the working set is free space, so most blocks end here without their voxels being read. Survivors
+// are appended to a work queue (block, slot, the eight corner-block slots and owners), which decouples meshing from the
+// list order: surface blocks are clustered in the list, and a warp that drew four of them used to serialise them.
 template <bool SHARDED>
-__global__ void __launch_bounds__(MC_THREADS)
-marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int* __restrict__ list,
-                      const int* __restrict__ list_count, const int full_map, unsigned long long* __restrict__ out_offset,
-                      int* __restrict__ out_count) {
-  __shared__ float s_tile[MC_WARPS][TILE_PAD];
-  __shared__ int s_nb[MC_WARPS][8];
-  __shared__ int s_nbo[MC_WARPS][8];
-  __shared__ unsigned short s_list[MC_WARPS][BLOCK_VOX * 5];   // candidate triangles of the block in flight
-  __shared__ signed char s_tri[256 * 16];
-  __shared__ unsigned char s_ntri[256];
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int i = tid; i < 256 * 16; i += MC_THREADS) s_tri[i] = c_tri[i >> 4][i & 15];
-  for (int i = tid; i < 256; i += MC_THREADS) s_ntri[i] = c_ntri[i];
-  __syncthreads();
-
+__global__ void __launch_bounds__(256)
+mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int* __restrict__ list,
+                 const int* __restrict__ list_count, const int full_map, unsigned long long* __restrict__ out_offset,
+                 int* __restrict__ out_count, McWork* __restrict__ queue, McQueueCtl* __restrict__ ctl) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n = min(*list_count, D.list_cap);
-  const bool color = S.use_color != 0;
-  const int gwarp = blockIdx.x * MC_WARPS + wid, nwarps = gridDim.x * MC_WARPS;
-  float* tile = s_tile[wid];
-  unsigned long long my_tris = 0;
-
-  // halo cells handled by this lane, the same for every block: tile offset << 12 | corner-block index << 9 | voxel in that block
-  int halo[7];
-#pragma unroll
-  for (int h = 0; h < 7; h++) {
-    const int c = h * 32 + lane;
-    int tx, ty, tz;
-    if (c < 81) { tx = 8; ty = c / 9; tz = c - ty * 9; }
-    else if (c < 153) { const int q = c - 81; tx = q / 9; ty = 8; tz = q - tx * 9; }
-    else { const int q = c - 153; tx = q >> 3; ty = q & 7; tz = 8; }
-    const int m = (tx >> 3) | ((ty >> 3) << 1) | ((tz >> 3) << 2);
-    halo[h] = c < 217 ? ((((tx * TILE + ty) * TILE + tz) << 12) | (m << 9) | ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))) : -1;
-  }
-
-  // The list is consumed four blocks at a time per warp: lane group g = lane >> 3 resolves block base+g and its seven
-  // +x/+y/+z neighbours (one lock-free probe per lane) and reads their negative-voxel counters (maintained by the
-  // integrate kernel). A block is meshed only if, among the blocks its 9^3 tile draws from, some voxel is negative and
-  // some is not — otherwise every cube index is 0 or 255 and the reference emits nothing for it either. In a room scan
-  // most of the working set is free space, so most blocks end here without their voxels being read.
   for (int base = gwarp * 4; base < n; base += nwarps * 4) {
     const int grp = lane >> 3, sub = lane & 7;
     const int item = base + grp;
-    int entry = -1, slot = -1;
-    McBlock B;
-    B.bx = B.by = B.bz = 0; B.tile = tile; B.nb_slot = s_nb[wid]; B.nb_owner = s_nbo[wid];
+    int slot = -1, bx = 0, by = 0, bz = 0;
     if (item < n) {
-      entry = list[item];
+      const int entry = list[item];
       const u64 key = D.map.keys[entry];
       slot = D.map.slots[entry];
-      unpack_key(key, B.bx, B.by, B.bz);
+      unpack_key(key, bx, by, bz);
     }
     // a neighbour counts only if it is in the same list (this frame's working set, tsdf.cu:930,957-969) or, for
     // full-map extraction, allocated at all
     int nb = -1, nb_owner = SHARDED ? (int)S.shard_rank : 0, nneg = 0;
     if (sub == 0) { nb = slot; if (slot >= 0) nneg = D.neg_count[slot]; }
     else if (slot >= 0) {
-      const int nx = B.bx + (sub & 1), ny = B.by + ((sub >> 1) & 1), nz = B.bz + ((sub >> 2) & 1);
+      const int nx = bx + (sub & 1), ny = by + ((sub >> 1) & 1), nz = bz + ((sub >> 2) & 1);
       if (key_in_range(nx, ny, nz)) {
         const u64 nk = pack_key(nx, ny, nz);
         if (SHARDED) {
@@ -313,33 +294,98 @@ marching_cubes_kernel(const StaticParams S, const uint32_t frame, const DeviceVi
     const unsigned b_pos = __ballot_sync(0xffffffffu, nb >= 0 && nneg < BLOCK_VOX);
     const bool need = slot >= 0 && ((b_neg >> gsh) & 0xFFu) != 0 && ((b_pos >> gsh) & 0xFFu) != 0;
     if (sub == 0 && slot >= 0 && !need) { out_offset[slot] = 0; out_count[slot] = 0; }
-    unsigned work = __ballot_sync(0xffffffffu, need && sub == 0);
-
-    while (work) {
-      const int src = __ffs(work) - 1;           // first lane of the group whose block is meshed now
-      work &= work - 1;
-      const int cur_slot = __shfl_sync(0xffffffffu, slot, src);
-      McBlock C;
-      C.bx = __shfl_sync(0xffffffffu, B.bx, src); C.by = __shfl_sync(0xffffffffu, B.by, src); C.bz = __shfl_sync(0xffffffffu, B.bz, src);
-      C.tile = tile; C.nb_slot = s_nb[wid]; C.nb_owner = s_nbo[wid];
-      const int my_nb = __shfl_sync(0xffffffffu, nb, src + (lane & 7));
-      const int my_nbo = __shfl_sync(0xffffffffu, nb_owner, src + (lane & 7));
-      const unsigned present = (b_present >> src) & 0xFFu;
-      __syncwarp();                              // previous block's readers of s_nb / tile / list are done
-      if (lane < 8) { s_nb[wid][lane] = my_nb; s_nbo[wid][lane] = my_nbo; }
-      __syncwarp();
-      my_tris += (unsigned long long)mesh_block<SHARDED>(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
+    // one queue reservation per warp
+    const unsigned lead = __ballot_sync(0xffffffffu, need && sub == 0);
+    if (lead) {
+      int qbase = 0;
+      if (lane == 0) qbase = atomicAdd(&ctl->count, __popc(lead));
+      qbase = __shfl_sync(0xffffffffu, qbase, 0);
+      if (need) {
+        McWork* w = queue + qbase + __popc(lead & ((1u << (grp * 8)) - 1));
+        w->nb[sub] = nb;
+        if (SHARDED) w->owner[sub] = (unsigned char)nb_owner;
+        if (sub == 0) { w->bx = bx; w->by = by; w->bz = bz; w->slot = slot; w->present = (b_present >> gsh) & 0xFFu; }
+      }
     }
+  }
+}
+
+// ---- stage 2: mesh ----------------------------------------------------------------------------------------------------
+// Persistent warps pull blocks off the work queue (one atomicAdd per block) and mesh them: perfect balance whatever the
+// spatial clustering of surface blocks. The last thing the kernel does is clear the OTHER queue-control slot, which the
+// next launch pair will use (the two slots alternate, so no memset node is needed per frame).
+template <bool SHARDED>
+__global__ void __launch_bounds__(MC_THREADS)
+mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int full_map, unsigned long long* __restrict__ out_offset,
+               int* __restrict__ out_count, const McWork* __restrict__ queue, McQueueCtl* __restrict__ ctl, McQueueCtl* __restrict__ ctl_next,
+               const uint4* __restrict__ tables) {
+  __shared__ float s_tile[MC_WARPS][TILE_PAD];
+  __shared__ int s_nb[MC_WARPS][8];
+  __shared__ int s_nbo[MC_WARPS][8];
+  __shared__ unsigned short s_list[MC_WARPS][BLOCK_VOX * 5];   // candidate triangles of the block in flight
+  __shared__ __align__(16) signed char s_tri[256 * 16];
+  __shared__ __align__(16) unsigned char s_ntri[256];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int total = ctl->count;
+  if (blockIdx.x == 0 && tid == 0) { ctl_next->count = 0; ctl_next->head = 0; }
+  if ((int)blockIdx.x * MC_WARPS >= total) return;                 // nothing left for this CTA: skip the table copy too
+  // case tables: 4 KB + 256 B, copied as 16-byte words from a global copy (constant-bank byte loads serialise)
+  for (int i = tid; i < 256; i += MC_THREADS) reinterpret_cast<uint4*>(s_tri)[i] = tables[i];
+  for (int i = tid; i < 16; i += MC_THREADS) reinterpret_cast<uint4*>(s_ntri)[i] = tables[256 + i];
+  __syncthreads();
+
+  const bool color = S.use_color != 0;
+  float* tile = s_tile[wid];
+  unsigned long long my_tris = 0;
+
+  // halo cells handled by this lane, the same for every block: tile offset << 12 | corner-block index << 9 | voxel in that block
+  int halo[7];
+#pragma unroll
+  for (int h = 0; h < 7; h++) {
+    const int c = h * 32 + lane;
+    int tx, ty, tz;
+    if (c < 81) { tx = 8; ty = c / 9; tz = c - ty * 9; }
+    else if (c < 153) { const int q = c - 81; tx = q / 9; ty = 8; tz = q - tx * 9; }
+    else { const int q = c - 153; tx = q >> 3; ty = q & 7; tz = 8; }
+    const int m = (tx >> 3) | ((ty >> 3) << 1) | ((tz >> 3) << 2);
+    halo[h] = c < 217 ? ((((tx * TILE + ty) * TILE + tz) << 12) | (m << 9) | ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))) : -1;
+  }
+
+  for (;;) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&ctl->head, 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= total) break;
+    const McWork* w = queue + idx;
+    McBlock C;
+    C.bx = w->bx; C.by = w->by; C.bz = w->bz; C.tile = tile; C.nb_slot = s_nb[wid]; C.nb_owner = s_nbo[wid];
+    const int cur_slot = w->slot;
+    const unsigned present = w->present;
+    __syncwarp();                              // previous block's readers of s_nb / tile / list are done
+    if (lane < 8) { s_nb[wid][lane] = w->nb[lane]; s_nbo[wid][lane] = SHARDED ? (int)w->owner[lane] : 0; }
+    __syncwarp();
+    my_tris += (unsigned long long)mesh_block<SHARDED>(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
 
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count, int full_map,
                            unsigned long long* out_offset, int* out_count, int num_sms, cudaStream_t st) {
-  if (S.shard_count > 1 && D.peers)
-    marching_cubes_kernel<true><<<num_sms * 10, MC_THREADS, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count);
-  else
-    marching_cubes_kernel<false><<<num_sms * 10, MC_THREADS, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  McQueueCtl* ctl = D.mc_ctl + (*D.mc_parity & 1);
+  McQueueCtl* ctl_next = D.mc_ctl + ((*D.mc_parity & 1) ^ 1);
+  *D.mc_parity ^= 1;
+  const int fgrid = num_sms * 4;
+  const int mgrid = num_sms * 5;                 // 5 CTAs of 4 warps fit an SM (36.7 KB of shared memory each)
+  if (S.shard_count > 1 && D.peers) {
+    mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+  } else {
+    mc_filter_kernel<false><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+  }
 }
 
 }  // namespace vh
