@@ -68,7 +68,7 @@ typedef struct vh_params {
   int shard_rank, shard_count;  /* multi-GPU: this engine owns blocks with owner(key) == shard_rank            */
   int shard_group;              /* ownership granularity, blocks per axis; 0 = blocks_per_chunk (8): neighbours
                                    mostly share an owner, so few marching-cubes halo reads cross NVLink          */
-  int depth_tile_smem;          /* 1: stage per-block depth tiles through TMA/shared memory in integrate       */
+  int depth_tile_smem;          /* reserved (staging depth tiles in shared memory was measured not to pay: DESIGN.md 5.2) */
   uint64_t tri_arena_bytes;     /* triangle arena size (grows on demand); 0 = default 1 GiB. With mc_per_frame a
                                    second arena of the same size is held as the compaction target                */
 } vh_params;
