@@ -133,7 +133,7 @@ static int reset_map(vh_engine* e) {
   init_free_list_kernel<<<(nb + 255) / 256, 256, 0, e->stream>>>(D.map.free_list, nb);
   CK(cudaMemcpyAsync(D.map.free_top, &nb, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0;
+  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0; e->forced_syncs = 0;
   memset(e->h_block, 0, sizeof(*e->h_block));
   return VH_OK;
 }
@@ -386,6 +386,7 @@ int make_room(vh_engine* e) {
   const unsigned long long projected = top + per_frame * (unsigned long long)(behind + 2);
   if (projected <= e->D.arena_cap && behind < 256) return VH_OK;
   CK(cudaStreamSynchronize(e->stream));
+  e->forced_syncs++;
   int rc = finish_sync(e);
   if (rc != VH_OK) return rc;
   if (e->known_arena_top + per_frame * 2 <= e->D.arena_cap) return VH_OK;
@@ -580,6 +581,7 @@ int vh_get_stats(vh_engine* e, vh_stats* out) {
   out->arena_triangles = e->h_block->arena_top;
   out->debug_mismatches = e->h_block->c.pad[0];
   out->arena_compactions = e->compactions;
+  out->forced_syncs = e->forced_syncs;
   if (e->frames > 0) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) out->ms_upload = ms;

@@ -51,7 +51,7 @@ struct vh_engine {
   // arena compaction: spare arena (ping-pong) and scan scratch
   vh_triangle* arena_spare = nullptr;
   unsigned long long *d_scan_in = nullptr, *d_scan_out = nullptr; void* d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
-  uint64_t compactions = 0;
+  uint64_t compactions = 0, forced_syncs = 0;
   int mc_parity = 0;                    // which McQueueCtl slot the next marching-cubes launch uses
   // multi-GPU (vh_shard.cu)
   vh_shard_state* shard = nullptr;
