@@ -55,6 +55,20 @@ def test_engine_matches_reference_golden(name, vh, synth):
         assert cs["sum_w"] == g["checksum"][1] and cs["n_observed"] == g["checksum"][2] and cs["n_negative"] == g["checksum"][3]
 
 
+def test_general_colour_path_matches_golden(vh, synth, monkeypatch):
+    """weights above 4096 switch the integrate kernel from the short exact colour average to the general division
+    sequence; VH_INTEGRATE_EXACT_COLOR=1 forces that variant from the first frame."""
+    monkeypatch.setenv("VH_INTEGRATE_EXACT_COLOR", "1")
+    name = "g8_color_holes"
+    case, g = CASES[name], load_golden(name)
+    sc = synth.Scene(**case["scene"])
+    with vh.TsdfEngine(engine_params(vh, sc, case)) as eng:
+        for i in range(case["frames"]):
+            eng.processFrame(*sc.frame(i))
+        assert_voxels_match(eng, g["keys"], g["sdf"], g["weight"], g["rgb"], True)
+        assert_triangles_match(*eng.triangles(), g["tri_xyz"], g["tri_rgb"], True)
+
+
 def run_pair(vh, ob, sc, case, frames, check_every=1, **eng_over):
     o = ob.Oracle(oracle_params(ob, sc, case))
     color = bool(case["scene"].get("color"))

@@ -133,7 +133,7 @@ static int reset_map(vh_engine* e) {
   init_free_list_kernel<<<(nb + 255) / 256, 256, 0, e->stream>>>(D.map.free_list, nb);
   CK(cudaMemcpyAsync(D.map.free_top, &nb, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0; e->forced_syncs = 0;
+  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0; e->forced_syncs = 0; e->integrate_launches = 0;
   memset(e->h_block, 0, sizeof(*e->h_block));
   return VH_OK;
 }
@@ -175,6 +175,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   S.shard_group = p->shard_group > 0 ? p->shard_group : p->blocks_per_chunk;
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '2' && v[0] <= '4') ? v[0] - '0' : 4; }   // tuning knobs
+  { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
   // approximate-projection error bound (vh_integrate.cu, gate4): 6.9e-7 px per pixel of image extent
   S.round_eps = 7.5e-7f * (float)std::max(p->width, p->height) + 2e-5f;
@@ -325,6 +326,7 @@ int enqueue_stages(vh_engine* e, bool do_alloc) {
   launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
   if (do_alloc) launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
   CK(cudaEventRecord(e->ev[2], e->stream));
+  e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->P.mc_per_frame)
@@ -508,6 +510,7 @@ int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb)
   CK(cudaMemsetAsync(&e->D.counters->voxel_updates, 0, sizeof(unsigned long long), e->stream));
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
   launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, nullptr, e->F.frame, e->stream);
+  e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, e->D, e->num_sms, e->stream);
   e->S.use_color = keep;
   int rc = enqueue_readback(e);

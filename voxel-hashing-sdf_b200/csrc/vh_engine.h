@@ -36,6 +36,7 @@ struct StaticParams {
   int shard_group;                // ownership granularity in blocks per axis
   float round_eps;                // distance from a .5 pixel tie below which integrate re-projects with IEEE divisions
   int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
+  uint32_t weight_bound;          // upper bound of any voxel weight after the coming integrate launch (= launches since reset)
   int integrate_two_steps;        // tuning: 1 = gate/load/update two steps of a block together, 0 = one step at a time (default)
   int integrate_ctas_per_sm;      // resident 256-thread CTAs per SM the integrate kernel is compiled for (2, 3 or 4; default 4)
 };

@@ -52,6 +52,8 @@ struct vh_engine {
   vh_triangle* arena_spare = nullptr;
   unsigned long long *d_scan_in = nullptr, *d_scan_out = nullptr; void* d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
   uint64_t compactions = 0, forced_syncs = 0;
+  uint32_t integrate_launches = 0;      // since the last reset: bounds every voxel weight
+  uint32_t weight_bound_bias = 0;       // env VH_INTEGRATE_EXACT_COLOR=1: pretend weights are large (forces the general colour path)
   int mc_parity = 0;                    // which McQueueCtl slot the next marching-cubes launch uses
   // multi-GPU (vh_shard.cu)
   vh_shard_state* shard = nullptr;

@@ -282,6 +282,7 @@ int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, c
   launch_pack_frame(e->cur_depth, e->cur_rgb, px, (int)npx, D.counters, e->F.frame, e->stream);
   launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
   CK(cudaEventRecord(e->ev[2], e->stream));
+  e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->P.mc_per_frame) {
