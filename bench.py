@@ -293,6 +293,10 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     ach = bytes_int / (ms_int * 1e-3) / 1e9 if ms_int > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "integrate_traffic.json")
+    if os.path.exists(tpath) and args.config == "C2" and color:
+        tj = json.load(open(tpath)); traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
 
     h2d = W * H * 4 + (W * H * 3 if color else 0) + 64
     d2h = 104
@@ -303,15 +307,15 @@ def run_ours(args):
         "config": config_dict(args, cfg, sc, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * FRAMES_PER_STEP, "d2h_bytes_per_step": d2h * FRAMES_PER_STEP,
                 "call": "vh_integrate (GpuTsdfGenerator::processFrame drop-in), pinned host depth+rgb, synchronous per frame"},
-        "gpu_launches": 3 * n_timed if not args.no_mc else 2 * n_timed,
+        "gpu_launches": (5 if not args.no_mc else 3) * n_timed,      # pack, allocate, integrate (+ mc_filter, mc_mesh) per frame
         "voxel_updates_per_sec": sum_over_ranks(float(acc["updates"])) / (ms_value / 1000.0),
         "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "triangles": tris_per_frame,
                       "ms_alloc": ms_alloc, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated,
                       "arena_compactions_in_500_frames": int(st_last.arena_compactions)},
         "roofline": {"kernel": "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": None,
+                     "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int},
-        "roofline_mc": {"kernel": "vh::marching_cubes_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
+        "roofline_mc": {"kernel": "vh::mc_filter_kernel + vh::mc_mesh_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
                         "peak": peak, "unit": "GB/s", "algorithmic_bytes_per_launch": bytes_mc, "avg_launch_ms": ms_mc},
         "clocks": clocks,
     }

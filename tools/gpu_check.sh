@@ -13,8 +13,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:integrate_kernel -s 120 -c 2 -f -o $OUT/prof_integrate_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_integrate_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:marching_cubes_kernel -s 120 -c 2 -f -o $OUT/prof_mc_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:mc_mesh_kernel -s 120 -c 2 -f -o $OUT/prof_mc_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_mc_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:mc_filter_kernel -s 120 -c 2 -f -o $OUT/prof_mcfilter_$TAG \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_mcfilter_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:alloc_visible_kernel -s 120 -c 2 -f -o $OUT/prof_alloc_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_alloc_$TAG.log 2>&1
 tail -n 3 $OUT/pytest_gpu_$TAG.log; tail -n 2 $OUT/smoke_$TAG.log; tail -c 600 $OUT/bench_$TAG.log

@@ -100,6 +100,7 @@ static int free_engine(vh_engine* e) {
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_depth[i]); cudaFree(e->d_rgb[i]); cudaFree(e->d_px[i]);
     if (e->ev_uploaded[i]) cudaEventDestroy(e->ev_uploaded[i]);
+    if (e->ev_rgb[i]) cudaEventDestroy(e->ev_rgb[i]);
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
   }
   for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -176,6 +177,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '2' && v[0] <= '4') ? v[0] - '0' : 4; }   // tuning knobs
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
+  { const char* v = getenv("VH_INTEGRATE_PREFETCH"); S.integrate_prefetch = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
   // approximate-projection error bound (vh_integrate.cu, gate4): 6.9e-7 px per pixel of image extent
   S.round_eps = 7.5e-7f * (float)std::max(p->width, p->height) + 2e-5f;
@@ -237,6 +239,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
             cudaHostAlloc((void**)&e->h_block, sizeof(*e->h_block), cudaHostAllocDefault) == cudaSuccess;
   for (int i = 0; i < 2 && ok; i++)
     ok = cudaEventCreateWithFlags(&e->ev_uploaded[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_rgb[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
   if (!ok) { free_engine(e); return fail(VH_ERR_CUDA, "CUDA Error: stream/event creation failed"); }
@@ -319,12 +322,20 @@ static int compact_arena(vh_engine* e, unsigned long long need) {
 }
 
 // ---- frame pipeline -----------------------------------------------------------------------------
-int enqueue_stages(vh_engine* e, bool do_alloc) {
+int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t rgb_ready) {
   DeviceView& D = e->D;
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
-  // first kernel of the frame: packs {depth, rgb} records for integrate and resets the frame's counters
-  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
-  if (do_alloc) launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
+  if (do_alloc && rgb_ready) {
+    // host frames: the ray pass needs only the depth image, so it runs while the colour image is still uploading
+    CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
+    launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
+    CK(cudaStreamWaitEvent(e->stream, rgb_ready, 0));
+    launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, D.counters, e->F.frame, e->stream, 1);
+  } else {
+    // first kernel of the frame: packs {depth, rgb} records for integrate and resets the frame's counters
+    launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
+    if (do_alloc) launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
+  }
   CK(cudaEventRecord(e->ev[2], e->stream));
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
@@ -406,8 +417,12 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
     const int b = e->ring & 1; e->ring++;
     if (e->buf_used[b]) CK(cudaStreamWaitEvent(e->upload, e->ev_consumed[b], 0));     // previous reader of this buffer is done
     CK(cudaMemcpyAsync(e->d_depth[b], depth, npx * sizeof(float), cudaMemcpyHostToDevice, e->upload));
-    if (rgb && e->S.use_color) CK(cudaMemcpyAsync(e->d_rgb[b], rgb, npx * 3, cudaMemcpyHostToDevice, e->upload));
     CK(cudaEventRecord(e->ev_uploaded[b], e->upload));
+    const bool with_rgb = rgb && e->S.use_color;
+    if (with_rgb) {
+      CK(cudaMemcpyAsync(e->d_rgb[b], rgb, npx * 3, cudaMemcpyHostToDevice, e->upload));
+      CK(cudaEventRecord(e->ev_rgb[b], e->upload));
+    }
     CK(cudaStreamWaitEvent(e->stream, e->ev_uploaded[b], 0));
     e->cur_depth = e->d_depth[b];
     e->cur_rgb = (rgb && e->S.use_color) ? e->d_rgb[b] : nullptr;
@@ -416,7 +431,7 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
     setup_frame(e, c2w);
     const int keep = e->S.use_color;   // colour only when the caller supplied an image
     e->S.use_color = e->cur_rgb ? keep : 0;
-    rc = enqueue_stages(e, true);
+    rc = enqueue_stages(e, true, with_rgb ? e->ev_rgb[b] : nullptr);
     e->S.use_color = keep;
     if (rc != VH_OK) return rc;
     CK(cudaEventRecord(e->ev_consumed[b], e->stream));
@@ -427,7 +442,7 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
     setup_frame(e, c2w);
     const int keep = e->S.use_color;
     e->S.use_color = e->cur_rgb ? keep : 0;
-    rc = enqueue_stages(e, true);
+    rc = enqueue_stages(e, true, nullptr);
     e->S.use_color = keep;
     if (rc != VH_OK) return rc;
   }

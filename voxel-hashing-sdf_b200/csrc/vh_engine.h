@@ -37,6 +37,7 @@ struct StaticParams {
   float round_eps;                // distance from a .5 pixel tie below which integrate re-projects with IEEE divisions
   int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
   uint32_t weight_bound;          // upper bound of any voxel weight after the coming integrate launch (= launches since reset)
+  int integrate_prefetch;         // tuning: 1 = prefetch a step's plane lines to L1 before its gate
   int integrate_two_steps;        // tuning: 1 = gate/load/update two steps of a block together, 0 = one step at a time (default)
   int integrate_ctas_per_sm;      // resident 256-thread CTAs per SM the integrate kernel is compiled for (2, 3 or 4; default 4)
 };
@@ -116,7 +117,7 @@ struct DeviceView {
 // kernels (defined in the .cu files)
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st);
 void launch_pack_frame(const float* d_depth, const uint8_t* d_rgb, uint2* d_out, int npx, FrameCounters* reset_counters, uint32_t frame,
-                       cudaStream_t st);
+                       cudaStream_t st, int stamp_only = 0);
 void launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* d_frame_px, bool color, const DeviceView& D, int num_sms,
                       cudaStream_t st);
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count,

@@ -32,7 +32,7 @@ struct vh_engine {
   uint8_t* d_rgb[2] = {nullptr, nullptr};
   uint2* d_px[2] = {nullptr, nullptr};     // packed {depth, rgb} records the integrate kernel reads
   int px_ring = 0;
-  cudaEvent_t ev_uploaded[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_uploaded[2] = {nullptr, nullptr}, ev_rgb[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   bool buf_used[2] = {false, false};
   int ring = 0;
   const float* cur_depth = nullptr;     // device pointers the stage calls operate on
@@ -71,7 +71,7 @@ void setup_frame(vh_engine* e, const float* c2w);
 void shard_release(vh_engine* e);               // vh_shard.cu: called by vh_destroy
 int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out, unsigned long long total);   // ordered soup of mb's blocks -> host
 extern "C" {
-int enqueue_stages(vh_engine* e, bool do_alloc);
+int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t rgb_ready);
 int enqueue_readback(vh_engine* e);
 int finish_sync(vh_engine* e);
 int make_room(vh_engine* e);
