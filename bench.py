@@ -266,12 +266,12 @@ def run_ours(args):
 
     # ---- per-kernel profile pass (untimed for the headline): CUDA-event time of every stage of every frame ----
     eng.reset()
-    acc = dict(alloc=0.0, integrate=0.0, mc=0.0, upload=0.0, updates=0, visible=0, tris=0)
+    acc = dict(alloc=0.0, integrate=0.0, mc=0.0, upload=0.0, updates=0, visible=0, tris=0, culled=0)
     for i in frames_of(n_timed):
         eng.integrate_device(dptr(d_depth, i), rgb_dev(i), poses[i])
         s = eng.stats()
         acc["alloc"] += s.ms_alloc; acc["integrate"] += s.ms_integrate; acc["mc"] += s.ms_mc
-        acc["updates"] += s.voxel_updates; acc["visible"] += s.visible_blocks; acc["tris"] += s.triangles
+        acc["updates"] += s.voxel_updates; acc["visible"] += s.visible_blocks; acc["tris"] += s.triangles; acc["culled"] += s.culled_blocks
     clocks = sampler.stop() if sampler else None
     st_last = eng.stats()
     allocated = st_last.allocated_blocks
@@ -309,7 +309,8 @@ def run_ours(args):
                 "call": "vh_integrate (GpuTsdfGenerator::processFrame drop-in), pinned host depth+rgb, synchronous per frame"},
         "gpu_launches": (5 if not args.no_mc else 3) * n_timed,      # pack, allocate, integrate (+ mc_filter, mc_mesh) per frame
         "voxel_updates_per_sec": sum_over_ranks(float(acc["updates"])) / (ms_value / 1000.0),
-        "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "triangles": tris_per_frame,
+        "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "blocks_discarded_whole_by_integrate": acc["culled"] / n_timed,
+                      "triangles": tris_per_frame,
                       "ms_alloc": ms_alloc, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated,
                       "arena_compactions_in_500_frames": int(st_last.arena_compactions)},
         "roofline": {"kernel": "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

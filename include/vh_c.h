@@ -85,6 +85,7 @@ typedef struct vh_stats {
   uint64_t debug_mismatches;    /* with env VH_INTEGRATE_VERIFY=1: fast-path vs IEEE-path disagreements in the last frame (must be 0) */
   uint64_t arena_compactions;   /* times the triangle arena was compacted (superseded per-block meshes dropped) */
   uint64_t forced_syncs;        /* times an asynchronous call had to drain the stream to bound arena use */
+  uint64_t culled_blocks;       /* visible blocks of the last frame the integrate kernel discarded whole (provably no update) */
 } vh_stats;
 
 /* vertex layout of the triangle soup: the reference's Vertex (tsdf.cuh:65-77), 16 bytes */

@@ -64,7 +64,7 @@ class VhStats(C.Structure):
                 ("voxel_updates", C.c_uint64), ("voxel_updates_total", C.c_uint64),
                 ("triangles", C.c_uint64), ("arena_triangles", C.c_uint64),
                 ("ms_upload", C.c_float), ("ms_alloc", C.c_float), ("ms_integrate", C.c_float), ("ms_mc", C.c_float),
-                ("debug_mismatches", C.c_uint64), ("arena_compactions", C.c_uint64), ("forced_syncs", C.c_uint64)]
+                ("debug_mismatches", C.c_uint64), ("arena_compactions", C.c_uint64), ("forced_syncs", C.c_uint64), ("culled_blocks", C.c_uint64)]
 
 
 TRI_DTYPE = np.dtype([("xyz0", np.float32, 3), ("rgb0", np.uint8, 4), ("xyz1", np.float32, 3), ("rgb1", np.uint8, 4),

@@ -93,7 +93,7 @@ static int free_engine(vh_engine* e) {
   if (e->upload) cudaStreamSynchronize(e->upload);
   DeviceView& D = e->D;
   cudaFree(D.map.keys); cudaFree(D.map.slots); cudaFree(D.map.free_list); cudaFree(D.map.free_top); cudaFree(D.map.key_heap);
-  cudaFree(e->d_status); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.neg_count); cudaFree(D.mc_queue); cudaFree(D.mc_ctl); cudaFree(D.visible);
+  cudaFree(e->d_status); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.tile_max); cudaFree(D.sched); cudaFree(D.neg_count); cudaFree(D.mc_queue); cudaFree(D.mc_ctl); cudaFree(D.visible);
   cudaFree(D.arena); cudaFree(e->arena_spare); cudaFree(e->d_scan_in); cudaFree(e->d_scan_out); cudaFree(e->d_scan_tmp);
   cudaFree(D.tri_offset); cudaFree(D.tri_count);
   cudaFree(e->d_full_list); cudaFree(e->d_full_count); cudaFree(e->d_full_off); cudaFree(e->d_full_cnt); cudaFree(e->d_keys_tmp);
@@ -177,7 +177,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '2' && v[0] <= '4') ? v[0] - '0' : 4; }   // tuning knobs
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
-  { const char* v = getenv("VH_INTEGRATE_PREFETCH"); S.integrate_prefetch = (v && v[0] == '0') ? 0 : 1; }
+  { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
   // approximate-projection error bound (vh_integrate.cu, gate4): 6.9e-7 px per pixel of image extent
   S.round_eps = 7.5e-7f * (float)std::max(p->width, p->height) + 2e-5f;
@@ -211,6 +211,8 @@ int vh_create(const vh_params* p, vh_engine** out) {
   ALLOC(D.wgt, nb * BLOCK_VOX * sizeof(float));
   if (S.use_color) ALLOC(D.rgb, nb * BLOCK_VOX * sizeof(uchar4));
   ALLOC(D.neg_count, nb * sizeof(int));
+  ALLOC(D.sched, 8 * 32 * sizeof(int));
+  ALLOC(D.tile_max, (size_t)((p->width + 15) / 16) * ((p->height + 15) / 16) * sizeof(float));
   ALLOC(D.mc_queue, (size_t)D.list_cap * sizeof(McWork));
   ALLOC(D.mc_ctl, 2 * sizeof(McQueueCtl));
   ALLOC(D.visible, (size_t)D.list_cap * sizeof(int));
@@ -330,10 +332,10 @@ int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t rgb_ready) {
     CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
     launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
     CK(cudaStreamWaitEvent(e->stream, rgb_ready, 0));
-    launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, D.counters, e->F.frame, e->stream, 1);
+    launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, D.counters, e->F.frame, e->stream, 1);
   } else {
     // first kernel of the frame: packs {depth, rgb} records for integrate and resets the frame's counters
-    launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
+    launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
     if (do_alloc) launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
   }
   CK(cudaEventRecord(e->ev[2], e->stream));
@@ -524,7 +526,7 @@ int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb)
   e->S.use_color = e->cur_rgb ? keep : 0;
   CK(cudaMemsetAsync(&e->D.counters->voxel_updates, 0, sizeof(unsigned long long), e->stream));
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
-  launch_pack_frame(e->cur_depth, e->cur_rgb, px, e->P.width * e->P.height, nullptr, e->F.frame, e->stream);
+  launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, e->D.tile_max, e->D.sched, nullptr, e->F.frame, e->stream);
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, e->D, e->num_sms, e->stream);
   e->S.use_color = keep;
@@ -600,6 +602,7 @@ int vh_get_stats(vh_engine* e, vh_stats* out) {
   out->debug_mismatches = e->h_block->c.pad[0];
   out->arena_compactions = e->compactions;
   out->forced_syncs = e->forced_syncs;
+  out->culled_blocks = e->h_block->c.pad[1];
   if (e->frames > 0) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) out->ms_upload = ms;

@@ -37,7 +37,7 @@ struct StaticParams {
   float round_eps;                // distance from a .5 pixel tie below which integrate re-projects with IEEE divisions
   int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
   uint32_t weight_bound;          // upper bound of any voxel weight after the coming integrate launch (= launches since reset)
-  int integrate_prefetch;         // tuning: 1 = prefetch a step's plane lines to L1 before its gate
+  int integrate_cull;             // 1 (default): discard whole blocks behind everything seen in their footprint; 0: gate every voxel
   int integrate_two_steps;        // tuning: 1 = gate/load/update two steps of a block together, 0 = one step at a time (default)
   int integrate_ctas_per_sm;      // resident 256-thread CTAs per SM the integrate kernel is compiled for (2, 3 or 4; default 4)
 };
@@ -96,6 +96,8 @@ struct DeviceView {
   float* sdf;
   float* wgt;
   uchar4* rgb;
+  int* sched;                     // [8 * 32] work counters of the integrate kernel's block scheduler (zeroed by pack_frame_kernel)
+  float* tile_max;                // [ceil(H/16) * ceil(W/16)] maximum depth per 16x16-pixel tile of the current frame
   int* neg_count;                 // [pool_blocks] number of voxels with sdf < 0 per block, kept current by integrate_kernel
   int* visible;
   int list_cap;
@@ -116,8 +118,8 @@ struct DeviceView {
 
 // kernels (defined in the .cu files)
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st);
-void launch_pack_frame(const float* d_depth, const uint8_t* d_rgb, uint2* d_out, int npx, FrameCounters* reset_counters, uint32_t frame,
-                       cudaStream_t st, int stamp_only = 0);
+void launch_pack_frame(const StaticParams& S, const float* d_depth, const uint8_t* d_rgb, uint2* d_out, float* d_tile_max, int* d_sched,
+                       FrameCounters* reset_counters, uint32_t frame, cudaStream_t st, int stamp_only = 0);
 void launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* d_frame_px, bool color, const DeviceView& D, int num_sms,
                       cudaStream_t st);
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count,

@@ -279,7 +279,7 @@ int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, c
   // allocate (own blocks only) + integrate, then marching cubes between two barriers
   DeviceView& D = e->D;
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
-  launch_pack_frame(e->cur_depth, e->cur_rgb, px, (int)npx, D.counters, e->F.frame, e->stream);
+  launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, D.counters, e->F.frame, e->stream);
   launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
   CK(cudaEventRecord(e->ev[2], e->stream));
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
