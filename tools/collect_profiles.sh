@@ -4,7 +4,7 @@
 set -euo pipefail
 TAG="$1"; SRC=gpurun_out; DST=profiles/$TAG
 mkdir -p "$DST"
-for f in pytest_gpu smoke bench bench_ref nvidia_smi; do
+for f in pytest_gpu smoke bench bench_ref nvidia_smi sanitizer_memcheck sanitizer_racecheck; do
   for e in log txt; do [ -f "$SRC/${f}_$TAG.$e" ] && cp "$SRC/${f}_$TAG.$e" "$DST/$f.$e"; done
 done
 [ -f "$SRC/launches_$TAG.csv" ] && { cp "$SRC/launches_$TAG.csv" "$DST/ncu_launches.csv"; python tools/ncu_launch_shares.py "$SRC/launches_$TAG.csv" > "$DST/ncu_launch_shares.txt"; }

@@ -8,6 +8,9 @@ nvidia-smi > $OUT/nvidia_smi_$TAG.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?" >> $OUT/smoke_$TAG.log
 timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.log 2>&1; echo "bench rc=$?" >> $OUT/bench_$TAG.log
+# memory and race checks of every kernel on the small smoke scene (the reference has none)
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/sanitizer_memcheck_$TAG.log 2>&1; echo "memcheck rc=$?" >> $OUT/sanitizer_memcheck_$TAG.log
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/sanitizer_racecheck_$TAG.log 2>&1; echo "racecheck rc=$?" >> $OUT/sanitizer_racecheck_$TAG.log
 timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/bench_ref_$TAG.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_$TAG.log 2>&1
