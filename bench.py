@@ -385,8 +385,9 @@ def run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, po
         out[label] = {"frames_per_sec": n_timed / (ms / 1000.0), "voxel_updates_per_sec": float(u.item()) / (ms / 1000.0),
                       "ms_per_frame": ms / n_timed, "allocated_blocks_all_shards": int(st.allocated_blocks)}
         eng.close()
-    out["note"] = ("single map, owner(block) = hash(block) mod n_gpus; per frame one ncclBroadcast of pose+depth+rgb from rank 0 (host buffers), "
-                   "replicated ray pass, 2 NCCL barriers around marching cubes; strong scaling (same 500-frame sequence at every n_gpus)")
+    out["note"] = ("single map, owner(block) = hash(block's 8^3-block cube) mod n_gpus; per frame one ncclBroadcast of pose+depth+rgb from rank 0 "
+                   "(pinned host buffers), replicated ray pass, marching-cubes halos read from the owner GPU over NVLink between two flag "
+                   "barriers; strong scaling (same 500-frame sequence at every n_gpus)")
     return out
 
 
