@@ -140,6 +140,38 @@ def test_unbounded_world_and_ray_cap(vh, ob, synth):
         assert_triangles_match(*eng.triangles(), *o.triangles(), False)
 
 
+def test_special_depth_values_and_partial_views(vh, ob, synth):
+    """NaN, +-inf, negative, zero, beyond-MaxDepth and sub-millimetre depth pixels, a camera close to a wall (blocks that
+    straddle the image border and the near plane) and a narrow truncation: the gates, the whole-block discard and the
+    allocation pass must treat every one of them as the reference's comparisons do (NaN passes `dv <= 0 || dv > max`)."""
+    sc = synth.Scene(width=320, height=240, room=(3.0, 2.5, 2.4), n_frames=24, radius_frac=0.42, spheres=((2.2, 1.2, 1.1, 0.35),), color=True)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.01, trunc=0.03, max_depth=2.5)
+    o = ob.Oracle(oracle_params(ob, sc, case))
+    rng = np.random.RandomState(5)
+    with vh.TsdfEngine(engine_params(vh, sc, case, num_buckets=1 << 18, pool_blocks=1 << 18, tri_arena_bytes=256 << 20)) as eng:
+        for i in range(6):
+            d, rgb, c2w = sc.frame(i)
+            d = d.copy()
+            r = rng.random_sample(d.shape)
+            d[r < 0.01] = np.nan
+            d[(r >= 0.01) & (r < 0.02)] = np.inf
+            d[(r >= 0.02) & (r < 0.03)] = -np.inf
+            d[(r >= 0.03) & (r < 0.04)] = -1.5
+            d[(r >= 0.04) & (r < 0.05)] = 7.0            # beyond MaxDepth
+            d[(r >= 0.05) & (r < 0.06)] = 1e-4
+            d[:16, :48] = np.nan                          # whole tiles of NaN / zero
+            d[100:132, 200:232] = 0.0
+            o.process_frame(d, rgb, c2w)
+            eng.processFrame(d, rgb, c2w)
+            st = eng.stats()
+            assert key_set(eng.visible_keys()) == key_set(o.visible_keys()), f"visible set differs in frame {i}"
+            assert (st.voxel_updates, st.triangles) == (o.last_updates, o.last_triangles), f"frame {i}"
+        keys = o.all_keys()
+        sdf, w, rgb_, _ = o.get_blocks(keys)
+        assert_voxels_match(eng, keys, sdf, w, rgb_, True)
+        assert_triangles_match(*eng.triangles(), *o.triangles(), True)
+
+
 def test_stage_entry_points_with_oracle_visible_list(vh, ob, synth):
     """integrate and marching cubes driven by a visible list produced by the ORACLE."""
     case = CASES["g8_color_holes"]
