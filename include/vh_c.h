@@ -78,7 +78,7 @@ typedef struct vh_stats {
   uint32_t visible_blocks;      /* |visible set| of the last frame (reference h_heapBlockCounter) */
   uint32_t allocated_blocks;    /* blocks ever allocated in the map */
   uint64_t voxel_updates;       /* voxels whose weight was incremented in the last frame */
-  uint64_t voxel_updates_total;
+  uint64_t voxel_updates_total; /* voxel updates since vh_create / vh_reset */
   uint64_t triangles;           /* valid triangles emitted for the last frame's working set */
   uint64_t arena_triangles;     /* triangles currently held in the arena (live + superseded) */
   float ms_upload, ms_alloc, ms_integrate, ms_mc;   /* CUDA-event times of the last frame's stages */

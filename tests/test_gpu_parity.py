@@ -280,6 +280,7 @@ def test_full_size_properties_5mm(vh, synth):
         ca, cb = a.checksum(), b.checksum()
         assert all(ca[k] == cb[k] for k in ("sum_w", "n_observed", "n_negative")) and abs(ca["sum_sdf"] - cb["sum_sdf"]) <= 1e-9 * abs(ca["sum_sdf"])   # deterministic map (double sums are order-dependent)
         assert ca["sum_w"] == total_updates                                      # every update adds exactly 1 to one weight
+        assert a.stats().voxel_updates_total == total_updates
         keys = sort_keys(a.allocated_keys())[:2000]
         sdf, w, _, _ = a.download_blocks(keys, want_rgb=False)
         assert np.array_equal(w, np.round(w)) and w.min() >= 0

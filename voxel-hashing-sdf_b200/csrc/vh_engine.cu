@@ -236,6 +236,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   D.map.heap_counter = &e->d_status->heap_counter;
   D.overflow_frame = &e->d_status->overflow_frame;
   D.arena_top = &e->d_status->arena_top;
+  D.updates_total = &e->d_status->updates_total;
   bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->upload, cudaStreamNonBlocking) == cudaSuccess &&
             cudaHostAlloc((void**)&e->h_block, sizeof(*e->h_block), cudaHostAllocDefault) == cudaSuccess;
@@ -596,7 +597,7 @@ int vh_get_stats(vh_engine* e, vh_stats* out) {
   out->visible_blocks = (uint32_t)e->h_block->c.visible_count;
   out->allocated_blocks = (uint32_t)e->h_block->heap_counter;
   out->voxel_updates = e->h_block->c.voxel_updates;
-  out->voxel_updates_total = 0;
+  out->voxel_updates_total = e->h_block->updates_total;
   out->triangles = e->h_block->c.triangles;
   out->arena_triangles = e->h_block->arena_top;
   out->debug_mismatches = e->h_block->c.pad[0];

@@ -68,7 +68,8 @@ struct DeviceStatus {
   int engine_error;               // sticky: 1 = triangle arena overflow
   uint32_t overflow_frame;        // first frame whose marching cubes ran out of arena (0 = none); must follow engine_error
   unsigned long long arena_top;   // triangles reserved in the arena
-  unsigned long long pad[5];
+  unsigned long long updates_total;   // voxel updates since the last reset
+  unsigned long long pad[4];
 };
 
 // What marching cubes needs from a shard of a multi-GPU map: its table and its voxel planes. Own pointers for the own
@@ -110,6 +111,7 @@ struct DeviceView {
   int* tri_count;                 // [pool_blocks]
   int* engine_error;              // sticky: 1 = arena overflow this frame
   uint32_t* overflow_frame;       // first frame that overflowed (0 = none)
+  unsigned long long* updates_total;   // running total of voxel updates (status block)
   const PeerTable* peers;         // multi-GPU: every shard's view (nullptr on a single GPU)
   McWork* mc_queue;               // [list_cap] marching-cubes work queue
   McQueueCtl* mc_ctl;             // [2] queue control, alternating per launch
