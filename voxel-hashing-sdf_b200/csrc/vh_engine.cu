@@ -526,6 +526,7 @@ int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb)
   const int keep = e->S.use_color;
   e->S.use_color = e->cur_rgb ? keep : 0;
   CK(cudaMemsetAsync(&e->D.counters->voxel_updates, 0, sizeof(unsigned long long), e->stream));
+  CK(cudaMemsetAsync(&e->D.counters->pad[0], 0, 2 * sizeof(unsigned long long), e->stream));     // verify mismatches, discarded blocks
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
   launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, e->D.tile_max, e->D.sched, nullptr, e->F.frame, e->stream);
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
