@@ -256,10 +256,32 @@ def test_full_map_mesh_superset_and_ply(vh, ob, synth, tmp_path):
         soup = (ref_xyz.reshape(-1, 3) * np.float32(case["vox_size"]))
         assert np.array_equal(verts["xyz"][faces.reshape(-1)], soup)
         assert len(np.unique(ref_xyz.reshape(-1, 3), axis=0)) == len(verts)
+        # numbering = tsdf2mesh's: ids in order of first appearance, the first occurrence's colour (tsdf.cu:1810-1821)
+        ref_rgb = eng.triangles(vh.VH_MESH_REF_PERSISTENT)[1].reshape(-1, 3)
+        pts = ref_xyz.reshape(-1, 3) + np.float32(0.0)
+        uniq, first, inv = np.unique(pts, axis=0, return_index=True, return_inverse=True)
+        rank = np.empty(len(uniq), np.int64); rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+        assert np.array_equal(faces.reshape(-1), rank[inv.reshape(-1)])
+        order = np.sort(first)
+        assert np.array_equal(verts["xyz"], pts[order] * np.float32(case["vox_size"]))
+        assert np.array_equal(verts["rgb"][:, :3], ref_rgb[order])
         ply = tmp_path / "model.ply"
         eng.SavePLY(str(ply))
         head = ply.read_text().split("end_header")[0]
         assert f"element vertex {len(verts)}" in head and f"element face {len(faces)}" in head and "comment stanford bunny" in head
+        # binary PLY: the same elements, exact
+        bply = tmp_path / "model_bin.ply"
+        eng.save_ply_binary(str(bply))
+        raw = bply.read_bytes()
+        hdr, body = raw.split(b"end_header\n", 1)
+        assert b"format binary_little_endian 1.0" in hdr and f"element vertex {len(verts)}".encode() in hdr
+        vrec = np.dtype([("xyz", "<f4", 3), ("rgb", "u1", 3)])
+        frec = np.dtype([("n", "u1"), ("idx", "<i4", 3)])
+        bv = np.frombuffer(body, vrec, len(verts))
+        bf = np.frombuffer(body, frec, len(faces), len(verts) * vrec.itemsize)
+        assert len(body) == len(verts) * 15 + len(faces) * 13
+        assert np.array_equal(bv["xyz"], verts["xyz"]) and np.array_equal(bv["rgb"], verts["rgb"][:, :3])
+        assert np.all(bf["n"] == 3) and np.array_equal(bf["idx"], faces)
 
 
 def test_full_size_properties_5mm(vh, synth):

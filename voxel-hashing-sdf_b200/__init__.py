@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "vh_integrate", "vh_integrate_async", "vh_wait_uploads", "vh_sync", "vh_integrate_device",
     "vh_upload_frame", "vh_stage_allocate", "vh_stage_integrate", "vh_stage_marching_cubes", "vh_set_visible",
     "vh_get_stats", "vh_stream", "vh_visible_keys", "vh_allocated_keys", "vh_download_blocks", "vh_voxel_checksum",
-    "vh_extract_mesh", "vh_save_ply", "vh_weld_mesh", "vh_host_alloc", "vh_host_free",
+    "vh_extract_mesh", "vh_save_ply", "vh_save_ply_binary", "vh_weld_mesh", "vh_host_alloc", "vh_host_free",
     "vh_map_create", "vh_map_destroy", "vh_map_insert", "vh_map_find", "vh_map_erase", "vh_map_size", "vh_map_keys",
     "vh_map_get_view",
     "vh_owner_of_block", "vh_shard_unique_id", "vh_shard_connect", "vh_integrate_sharded", "vh_shard_gather_mesh", "vh_shard_stats",
@@ -112,6 +112,7 @@ def load_library():
     L.vh_voxel_checksum.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.vh_extract_mesh.argtypes = [vp, ip, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.vh_save_ply.argtypes = [vp, C.c_char_p, ip]
+    L.vh_save_ply_binary.argtypes = [vp, C.c_char_p, ip]
     L.vh_weld_mesh.argtypes = [vp, ip, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.vh_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.vh_host_free.argtypes = [vp]
@@ -360,6 +361,9 @@ class TsdfEngine:
         _check(self.L.vh_save_ply(self.h, path.encode(), mode))
 
     save_ply = SavePLY
+
+    def save_ply_binary(self, path: str, mode=VH_MESH_REF_PERSISTENT):
+        _check(self.L.vh_save_ply_binary(self.h, path.encode(), mode))
 
 
 class BlockHashMap:

@@ -17,7 +17,6 @@
 #include <fstream>
 #include <mutex>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 #include "vh_engine_host.h"
@@ -792,8 +791,10 @@ int collect_blocks(vh_engine* e, int mode, MeshBlocks& mb) {
 
 }  // extern "C"
 
-// copy the triangle ranges of mb's blocks, in mb's order, into one host array of `total` triangles
-int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out, unsigned long long total) {
+// copy the triangle ranges of mb's blocks, in mb's order, into one array of `total` triangles: on the host (out) and/or left on
+// the device (*d_keep, to be cudaFree'd by the caller)
+int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out, unsigned long long total, vh_triangle** d_keep) {
+  if (d_keep) *d_keep = nullptr;
   const int n = (int)mb.key.size();
   if (total == 0 || n == 0) return VH_OK;
   std::vector<unsigned long long> dst((size_t)n);
@@ -811,8 +812,9 @@ int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out,
     launch_gather_triangles(mb.arena, d_src, d_dst, d_cnt, n, d_out, e->stream);
     ce = cudaStreamSynchronize(e->stream);
   }
-  if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, (size_t)total * sizeof(vh_triangle), cudaMemcpyDeviceToHost);
-  cudaFree(d_src); cudaFree(d_dst); cudaFree(d_cnt); cudaFree(d_out);
+  if (ce == cudaSuccess && out) ce = cudaMemcpy(out, d_out, (size_t)total * sizeof(vh_triangle), cudaMemcpyDeviceToHost);
+  cudaFree(d_src); cudaFree(d_dst); cudaFree(d_cnt);
+  if (ce != cudaSuccess || !d_keep) cudaFree(d_out); else *d_keep = d_out;
   if (ce != cudaSuccess) return fail(VH_ERR_CUDA, "CUDA Error: %s while gathering triangles", cudaGetErrorString(ce));
   return VH_OK;
 }
@@ -835,7 +837,7 @@ static int extract_mesh_locked(vh_engine* e, int mode, std::vector<vh_triangle>*
     cudaFree(mb.tmp_arena);
     return fail(VH_ERR_INVALID, "output capacity %llu < %llu triangles", (unsigned long long)cap, total);
   }
-  if (out) rc = gather_block_triangles(e, mb, out, total);
+  if (out) rc = gather_block_triangles(e, mb, out, total, nullptr);
   cudaFree(mb.tmp_arena);
   return rc;
 }
@@ -847,43 +849,32 @@ int vh_extract_mesh(vh_engine* e, int mode, vh_triangle* out, uint64_t cap, uint
   return extract_mesh_locked(e, mode, nullptr, out, cap, n);
 }
 
-// vertex dedupe on exact float xyz, first occurrence's colour wins, coordinates * vox_size (tsdf2mesh, tsdf.cu:1810-1821)
-struct XyzKey { float x, y, z; bool operator==(const XyzKey& o) const { return x == o.x && y == o.y && z == o.z; } };
-struct XyzHash {
-  size_t operator()(const XyzKey& k) const {
-    uint32_t a, b, c; const float x = k.x + 0.0f, y = k.y + 0.0f, z = k.z + 0.0f;   // -0 -> +0 so equal keys hash equally
-    memcpy(&a, &x, 4); memcpy(&b, &y, 4); memcpy(&c, &z, 4);
-    uint64_t h = (uint64_t)a * 0x9E3779B97F4A7C15ull ^ ((uint64_t)b << 21) * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)c * 0x165667B19E3779F9ull;
-    return (size_t)(h ^ (h >> 29));
-  }
-};
-
-static void weld(const std::vector<vh_triangle>& tris, float vox_size, std::vector<vh_vertex>& verts, std::vector<int32_t>& faces) {
-  std::unordered_map<XyzKey, int32_t, XyzHash> seen;
-  seen.reserve(tris.size() * 2);
-  faces.resize(tris.size() * 3);
-  for (size_t t = 0; t < tris.size(); t++)
-    for (int j = 0; j < 3; j++) {
-      const vh_vertex& v = tris[t].p[j];
-      auto it = seen.find(XyzKey{v.x, v.y, v.z});
-      if (it == seen.end()) {
-        const int32_t id = (int32_t)verts.size();
-        seen.emplace(XyzKey{v.x, v.y, v.z}, id);
-        vh_vertex s = v; s.x *= vox_size; s.y *= vox_size; s.z *= vox_size; s.pad = 0;
-        verts.push_back(s);
-        faces[3 * t + j] = id;
-      } else faces[3 * t + j] = it->second;
-    }
+// welded mesh of the whole map: ordered soup gathered on the device, welded there (vh_weld.cu), copied out once
+static int welded_mesh_locked(vh_engine* e, int mode, std::vector<vh_vertex>& v, std::vector<int32_t>& f) {
+  CK(cudaSetDevice(e->P.device));
+  CK(cudaStreamSynchronize(e->stream));
+  int rc = finish_sync(e);
+  if (rc != VH_OK) return rc;
+  MeshBlocks mb;
+  rc = collect_blocks(e, mode, mb);
+  if (rc != VH_OK) { cudaFree(mb.tmp_arena); return rc; }
+  unsigned long long total = 0;
+  for (int c : mb.cnt) total += (unsigned long long)c;
+  vh_triangle* d_soup = nullptr;
+  rc = gather_block_triangles(e, mb, nullptr, total, &d_soup);
+  cudaFree(mb.tmp_arena);
+  if (rc == VH_OK) rc = weld_on_device(e, d_soup, total, v, f);
+  cudaFree(d_soup);
+  return rc;
 }
 
 int vh_weld_mesh(vh_engine* e, int mode, vh_vertex* verts, uint64_t vcap, uint64_t* nv, int32_t* faces, uint64_t fcap, uint64_t* nf) {
   if (!e) return fail(VH_ERR_INVALID, "null engine");
+  if (mode != VH_MESH_REF_PERSISTENT && mode != VH_MESH_FULL_MAP) return fail(VH_ERR_INVALID, "unknown mesh mode %d", mode);
   std::lock_guard<std::mutex> lk(e->mtx);
-  std::vector<vh_triangle> tris;
-  int rc = extract_mesh_locked(e, mode, &tris, nullptr, 0, nullptr);
-  if (rc != VH_OK) return rc;
   std::vector<vh_vertex> v; std::vector<int32_t> f;
-  weld(tris, e->P.vox_size, v, f);
+  int rc = welded_mesh_locked(e, mode, v, f);
+  if (rc != VH_OK) return rc;
   if (nv) *nv = v.size();
   if (nf) *nf = f.size() / 3;
   if (verts) { if (vcap < v.size()) return fail(VH_ERR_INVALID, "vertex capacity too small"); memcpy(verts, v.data(), v.size() * sizeof(vh_vertex)); }
@@ -891,27 +882,37 @@ int vh_weld_mesh(vh_engine* e, int mode, vh_vertex* verts, uint64_t vcap, uint64
   return VH_OK;
 }
 
-int vh_save_ply(vh_engine* e, const char* path, int mode) {
+// ASCII: same header and default ostream number formatting as tsdf2mesh (tsdf.cu:1870-1885). Binary: the same elements as
+// binary_little_endian 1.0 (15-byte vertices, 13-byte faces), exact floats and a fraction of the size.
+static int save_ply(vh_engine* e, const char* path, int mode, bool binary) {
   if (!e || !path) return fail(VH_ERR_INVALID, "null argument");
+  if (mode != VH_MESH_REF_PERSISTENT && mode != VH_MESH_FULL_MAP) return fail(VH_ERR_INVALID, "unknown mesh mode %d", mode);
   std::lock_guard<std::mutex> lk(e->mtx);
-  std::vector<vh_triangle> tris;
-  int rc = extract_mesh_locked(e, mode, &tris, nullptr, 0, nullptr);
-  if (rc != VH_OK) return rc;
   std::vector<vh_vertex> v; std::vector<int32_t> f;
-  weld(tris, e->P.vox_size, v, f);
-  std::ofstream ply(path);
+  int rc = welded_mesh_locked(e, mode, v, f);
+  if (rc != VH_OK) return rc;
+  std::ofstream ply(path, binary ? std::ios::binary : std::ios::out);
   if (!ply) return fail(VH_ERR_IO, "cannot open %s", path);
-  // same header and default ostream number formatting as tsdf2mesh (tsdf.cu:1870-1885)
-  ply << "ply\nformat ascii 1.0\ncomment stanford bunny\nelement vertex " << v.size() << "\n";
+  ply << "ply\nformat " << (binary ? "binary_little_endian" : "ascii") << " 1.0\ncomment stanford bunny\nelement vertex " << v.size() << "\n";
   ply << "property float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n";
   ply << "element face " << f.size() / 3 << "\n";
   ply << "property list uchar int vertex_index\nend_header\n";
-  for (const auto& p : v) ply << p.x << " " << p.y << " " << p.z << " " << (int)p.r << " " << (int)p.g << " " << (int)p.b << "\n";
-  for (size_t t = 0; t < f.size() / 3; t++) ply << "3 " << f[3 * t] << " " << f[3 * t + 1] << " " << f[3 * t + 2] << "\n";
+  if (binary) {
+    std::vector<char> buf;
+    buf.reserve(v.size() * 15 + f.size() / 3 * 13);
+    for (const auto& p : v) { const char* q = reinterpret_cast<const char*>(&p); buf.insert(buf.end(), q, q + 15); }   // x y z r g b
+    for (size_t t = 0; t < f.size() / 3; t++) { buf.push_back(3); const char* q = reinterpret_cast<const char*>(&f[3 * t]); buf.insert(buf.end(), q, q + 12); }
+    ply.write(buf.data(), (std::streamsize)buf.size());
+  } else {
+    for (const auto& p : v) ply << p.x << " " << p.y << " " << p.z << " " << (int)p.r << " " << (int)p.g << " " << (int)p.b << "\n";
+    for (size_t t = 0; t < f.size() / 3; t++) ply << "3 " << f[3 * t] << " " << f[3 * t + 1] << " " << f[3 * t + 2] << "\n";
+  }
   ply.close();
   if (!ply) return fail(VH_ERR_IO, "write to %s failed", path);
   return VH_OK;
 }
+int vh_save_ply(vh_engine* e, const char* path, int mode) { return save_ply(e, path, mode, false); }
+int vh_save_ply_binary(vh_engine* e, const char* path, int mode) { return save_ply(e, path, mode, true); }
 
 int vh_host_alloc(void** p, size_t bytes) {
   if (!p) return fail(VH_ERR_INVALID, "null argument");

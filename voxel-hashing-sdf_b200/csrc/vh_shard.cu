@@ -372,7 +372,7 @@ int vh_shard_gather_mesh(vh_engine* e, int mode, vh_triangle* out, uint64_t cap,
   unsigned long long total = 0;
   for (int c : mb.cnt) total += (unsigned long long)c;
   std::vector<vh_triangle> tris((size_t)total);
-  rc = gather_block_triangles(e, mb, tris.data(), total);
+  rc = gather_block_triangles(e, mb, tris.data(), total, nullptr);
   cudaFree(mb.tmp_arena);
   if (rc != VH_OK) return rc;
   if (mode == VH_MESH_FULL_MAP) { rc = shard_barrier(e); if (rc != VH_OK) return rc; }   // nobody integrates while a peer still meshes
