@@ -368,7 +368,7 @@ def run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, po
         p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"],
                                 num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=(3 << 20) // world + (1 << 18),
                                 use_color=1 if color else 0, mc_per_frame=mc, device=local, shard_rank=rank, shard_count=world,
-                                tri_arena_bytes=(4 << 30) // world + (256 << 20))
+                                tri_arena_bytes=(4 << 30) // world + (1 << 30))
         eng = vh.TsdfEngine(p)
         ids = [vh.TsdfEngine.shard_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

@@ -372,6 +372,9 @@ int finish_sync(vh_engine* e) {
     CK(cudaStreamSynchronize(e->stream));
     int rc = compact_arena(e, std::max<unsigned long long>(hb->c.triangles * 2, 1ull << 20));
     if (rc != VH_OK) return rc;
+    if (e->shard)
+      return fail(VH_ERR_ARENA_FULL, "triangle arena overflowed in frame %u of a sharded map (a repair would need every GPU): raise tri_arena_bytes "
+                  "(arena grown to %llu triangles)", first_bad, (unsigned long long)e->D.arena_cap);
     if (first_bad != last)
       return fail(VH_ERR_ARENA_FULL, "triangle arena overflowed in frame %u while frames up to %u were in flight: blocks meshed in between are "
                   "incomplete until seen again; raise tri_arena_bytes or call vh_sync more often (arena grown to %llu triangles)",
