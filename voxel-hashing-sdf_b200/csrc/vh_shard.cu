@@ -82,7 +82,7 @@ struct vh_shard_state {
   size_t frame_bytes = 0;
   uint8_t* h_frame = nullptr;         // pinned staging of the same layout (rank 0 packs the caller's buffers here)
   int ring = 0;
-  cudaEvent_t consumed[2] = {nullptr, nullptr}; bool used[2] = {false, false};
+  cudaEvent_t consumed[2] = {nullptr, nullptr}, uploaded[2] = {nullptr, nullptr}, arrived[2] = {nullptr, nullptr}; bool used[2] = {false, false};
   int* d_token = nullptr;             // 1-int all-reduce (connect-time barrier)
   uint32_t* d_flags = nullptr;        // [MAX_SHARDS] arrival epochs written by the peers (and by this GPU) over NVLink
   uint32_t* peer_flags[MAX_SHARDS] = {};
@@ -94,6 +94,7 @@ void shard_release(vh_engine* e) {
   vh_shard_state* s = e->shard;
   if (!s) return;
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->upload) cudaStreamSynchronize(e->upload);
   for (int r = 0; r < s->count; r++)
     for (int k = 0; k < N_SHARED; k++)
       if (r != s->rank && s->mapped[r][k]) cudaIpcCloseMemHandle(s->mapped[r][k]);
@@ -101,7 +102,11 @@ void shard_release(vh_engine* e) {
   cudaFree(s->d_frame); cudaFree(s->d_token); cudaFree(s->d_flags);
   if (s->h_frame) cudaFreeHost(s->h_frame);
   if (s->h_pose) cudaFreeHost(s->h_pose);
-  for (int i = 0; i < 2; i++) if (s->consumed[i]) cudaEventDestroy(s->consumed[i]);
+  for (int i = 0; i < 2; i++) {
+    if (s->consumed[i]) cudaEventDestroy(s->consumed[i]);
+    if (s->uploaded[i]) cudaEventDestroy(s->uploaded[i]);
+    if (s->arrived[i]) cudaEventDestroy(s->arrived[i]);
+  }
   cudaFree(e->d_peers); e->d_peers = nullptr; e->D.peers = nullptr;
   delete s;
   e->shard = nullptr;
@@ -180,7 +185,11 @@ int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]) {
   CK(cudaMemset(s->d_token, 0, sizeof(int)));
   CK(cudaMalloc((void**)&s->d_flags, MAX_SHARDS * sizeof(uint32_t)));
   CK(cudaMemset(s->d_flags, 0, MAX_SHARDS * sizeof(uint32_t)));
-  for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->uploaded[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->arrived[i], cudaEventDisableTiming));
+  }
 
   // exchange IPC handles of what a peer's marching cubes needs to read
   ShardExport mine;
@@ -245,6 +254,10 @@ int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, c
   const bool with_rgb = e->S.use_color != 0;                      // group-wide: every rank was created with the same flag
   const size_t bytes = 64 + npx * 4 + (with_rgb ? npx * 3 : 0);
   CK(cudaEventRecord(e->ev[0], e->stream));
+  // Upload and broadcast run on the upload stream, double-buffered: frame k+1 travels (PCIe, then NVLink) while frame k is
+  // still being integrated and meshed; the compute stream only waits for the broadcast of its own frame.
+  cudaStream_t up = e->upload;
+  if (s->used[b]) CK(cudaStreamWaitEvent(up, s->consumed[b], 0));            // buffer b's previous frame has been consumed
   if (s->rank == 0) {
     // pinned caller buffers are copied straight into the broadcast buffer; pageable ones go through the pinned staging slot
     cudaPointerAttributes pa;
@@ -252,25 +265,28 @@ int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, c
                         (!with_rgb || !rgb || (cudaPointerGetAttributes(&pa, rgb) == cudaSuccess && pa.type == cudaMemoryTypeHost));
     cudaGetLastError();
     uint8_t* hbuf = s->h_frame + (size_t)b * s->frame_bytes;
-    if (s->used[b]) CK(cudaEventSynchronize(s->consumed[b]));    // slot b's previous frame (two frames ago) is done with the staging memory
+    if (s->used[b]) CK(cudaEventSynchronize(s->uploaded[b]));    // staging slot b's previous upload (two frames ago) has left the host
     memcpy(hbuf, c2w, 64);
-    CK(cudaMemcpyAsync(dbuf, hbuf, 64, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(dbuf, hbuf, 64, cudaMemcpyHostToDevice, up));
     if (pinned) {
-      CK(cudaMemcpyAsync(dbuf + 64, depth, npx * 4, cudaMemcpyHostToDevice, e->stream));
-      if (with_rgb) { if (rgb) CK(cudaMemcpyAsync(dbuf + 64 + npx * 4, rgb, npx * 3, cudaMemcpyHostToDevice, e->stream)); else CK(cudaMemsetAsync(dbuf + 64 + npx * 4, 0, npx * 3, e->stream)); }
+      CK(cudaMemcpyAsync(dbuf + 64, depth, npx * 4, cudaMemcpyHostToDevice, up));
+      if (with_rgb) { if (rgb) CK(cudaMemcpyAsync(dbuf + 64 + npx * 4, rgb, npx * 3, cudaMemcpyHostToDevice, up)); else CK(cudaMemsetAsync(dbuf + 64 + npx * 4, 0, npx * 3, up)); }
     } else {
       memcpy(hbuf + 64, depth, npx * 4);
       if (with_rgb) { if (rgb) memcpy(hbuf + 64 + npx * 4, rgb, npx * 3); else memset(hbuf + 64 + npx * 4, 0, npx * 3); }
-      CK(cudaMemcpyAsync(dbuf + 64, hbuf + 64, bytes - 64, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(dbuf + 64, hbuf + 64, bytes - 64, cudaMemcpyHostToDevice, up));
     }
+    CK(cudaEventRecord(s->uploaded[b], up));
   }
-  NK(g_nccl.Broadcast(dbuf, dbuf, bytes, ncclChar, 0, s->comm, e->stream));
+  NK(g_nccl.Broadcast(dbuf, dbuf, bytes, ncclChar, 0, s->comm, up));
+  CK(cudaEventRecord(s->arrived[b], up));
+  CK(cudaStreamWaitEvent(e->stream, s->arrived[b], 0));
   CK(cudaEventRecord(e->ev[1], e->stream));
   float pose[16];
   if (c2w) memcpy(pose, c2w, sizeof(pose));
   else {
-    CK(cudaMemcpyAsync(s->h_pose, dbuf, 64, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyAsync(s->h_pose, dbuf, 64, cudaMemcpyDeviceToHost, up));
+    CK(cudaStreamSynchronize(up));
     memcpy(pose, s->h_pose, sizeof(pose));
   }
   e->cur_depth = reinterpret_cast<const float*>(dbuf + 64);
