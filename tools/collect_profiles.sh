@@ -8,7 +8,7 @@ for f in pytest_gpu smoke bench bench_ref nvidia_smi sanitizer_memcheck sanitize
   for e in log txt; do [ -f "$SRC/${f}_$TAG.$e" ] && cp "$SRC/${f}_$TAG.$e" "$DST/$f.$e"; done
 done
 [ -f "$SRC/launches_$TAG.csv" ] && { cp "$SRC/launches_$TAG.csv" "$DST/ncu_launches.csv"; python tools/ncu_launch_shares.py "$SRC/launches_$TAG.csv" > "$DST/ncu_launch_shares.txt"; }
-METRICS='gpu__time_duration.sum|dram__bytes_read.sum|dram__bytes_write.sum|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|sm__warps_active.avg.pct_of_peak_sustained_active|launch__registers_per_thread|sm__throughput.avg.pct_of_peak_sustained_elapsed|l1tex__t_sector_hit_rate.pct|lts__t_sector_hit_rate.pct|smsp__inst_executed.sum|launch__occupancy_limit_registers|launch__occupancy_limit_shared_mem|launch__grid_size|launch__block_size|smsp__issue_active.avg.pct_of_peak_sustained_active|sm__cycles_active.avg|launch__shared_mem_per_block_static|lts__t_sectors_op_atom.sum|lts__t_sectors_op_red.sum|l1tex__t_bytes.sum|lts__t_bytes.sum'
+METRICS='gpu__time_duration.sum|dram__bytes_read.sum|dram__bytes_write.sum|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|sm__warps_active.avg.pct_of_peak_sustained_active|launch__registers_per_thread|sm__throughput.avg.pct_of_peak_sustained_elapsed|l1tex__t_sector_hit_rate.pct|lts__t_sector_hit_rate.pct|smsp__inst_executed.sum|launch__occupancy_limit_registers|launch__occupancy_limit_shared_mem|launch__grid_size|launch__block_size|smsp__issue_active.avg.pct_of_peak_sustained_active|sm__cycles_active.avg|launch__shared_mem_per_block_static|l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum|l1tex__t_requests_pipe_lsu_mem_global_op_red.sum|l1tex__t_sectors_pipe_lsu_mem_global_op_atom.sum|lts__t_sectors_op_atom.sum|lts__t_sectors_op_red.sum|lts__t_sectors_srcunit_tex_op_atom.sum|l1tex__t_bytes.sum|lts__t_bytes.sum'
 for k in integrate mc mcfilter alloc; do
   R="$SRC/prof_${k}_$TAG.ncu-rep"
   [ -f "$R" ] || continue
