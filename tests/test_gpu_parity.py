@@ -212,6 +212,37 @@ def test_async_pipeline_equals_sync(vh, synth):
         assert np.array_equal(a.triangles()[0], b.triangles()[0])
 
 
+def test_pinned_host_frames_equal_pageable(vh, synth):
+    """pinned caller buffers take a different route (the ray pass reads the depth samples straight from mapped host memory
+    while the images upload): same map as with pageable buffers, through both the synchronous and the async call."""
+    import ctypes as C
+    sc = synth.Scene(width=320, height=240, room=(5.0, 4.0, 2.6), n_frames=30, color=True, holes=0.02)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.02, trunc=0.1, max_depth=3.5)
+    frames = [sc.frame(i) for i in range(6)]
+    L = vh.load_library()
+    nd, nc = frames[0][0].nbytes, frames[0][1].nbytes
+    pd, pc = C.c_void_p(), C.c_void_p()
+    assert L.vh_host_alloc(C.byref(pd), nd * len(frames)) == 0 and L.vh_host_alloc(C.byref(pc), nc * len(frames)) == 0
+    try:
+        for i, (d, rgb, _) in enumerate(frames):
+            C.memmove(pd.value + i * nd, d.ctypes.data, nd); C.memmove(pc.value + i * nc, rgb.ctypes.data, nc)
+        with vh.TsdfEngine(engine_params(vh, sc, case)) as a, vh.TsdfEngine(engine_params(vh, sc, case)) as b, \
+                vh.TsdfEngine(engine_params(vh, sc, case)) as c:
+            for i, (d, rgb, c2w) in enumerate(frames):
+                a.processFrame(d, rgb, c2w)                                                       # pageable
+                assert L.vh_integrate(b.h, pd.value + i * nd, pc.value + i * nc, c2w.ctypes.data) == 0   # pinned, synchronous
+                c.integrate_async(pd.value + i * nd, pc.value + i * nc, c2w)                      # pinned, asynchronous
+            c.sync()
+            keys = sort_keys(a.allocated_keys())
+            for other in (b, c):
+                assert np.array_equal(keys, sort_keys(other.allocated_keys()))
+                for x, y in zip(a.download_blocks(keys), other.download_blocks(keys)):
+                    assert np.array_equal(x, y)
+                assert np.array_equal(a.triangles()[0], other.triangles()[0])
+    finally:
+        L.vh_host_free(pd); L.vh_host_free(pc)
+
+
 def test_empty_frames_and_errors(vh, synth):
     case = CASES["g8_color_holes"]
     sc = synth.Scene(**case["scene"])

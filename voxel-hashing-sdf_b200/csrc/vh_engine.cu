@@ -324,16 +324,21 @@ static int compact_arena(vh_engine* e, unsigned long long need) {
 }
 
 // ---- frame pipeline -----------------------------------------------------------------------------
-int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t rgb_ready) {
+int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEvent_t rgb_ready, const float* host_depth_mapped) {
   DeviceView& D = e->D;
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
-  if (do_alloc && rgb_ready) {
-    // host frames: the ray pass needs only the depth image, so it runs while the colour image is still uploading
+  if (do_alloc && (rgb_ready || host_depth_mapped)) {
+    // Host frames: the ray pass needs only ~3,000 depth samples. With a pinned (device-mapped) caller buffer it reads them
+    // straight from host memory and runs while BOTH images are still uploading; otherwise it waits for the depth upload
+    // and overlaps the colour upload only.
+    if (!host_depth_mapped && depth_ready) CK(cudaStreamWaitEvent(e->stream, depth_ready, 0));
     CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
-    launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
-    CK(cudaStreamWaitEvent(e->stream, rgb_ready, 0));
+    launch_alloc_visible(e->S, e->F, host_depth_mapped ? host_depth_mapped : e->cur_depth, D, e->stream);
+    if (host_depth_mapped && depth_ready) CK(cudaStreamWaitEvent(e->stream, depth_ready, 0));
+    if (rgb_ready) CK(cudaStreamWaitEvent(e->stream, rgb_ready, 0));
     launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, D.counters, e->F.frame, e->stream, 1);
   } else {
+    if (depth_ready) CK(cudaStreamWaitEvent(e->stream, depth_ready, 0));
     // first kernel of the frame: packs {depth, rgb} records for integrate and resets the frame's counters
     launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
     if (do_alloc) launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
@@ -428,7 +433,13 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
       CK(cudaMemcpyAsync(e->d_rgb[b], rgb, npx * 3, cudaMemcpyHostToDevice, e->upload));
       CK(cudaEventRecord(e->ev_rgb[b], e->upload));
     }
-    CK(cudaStreamWaitEvent(e->stream, e->ev_uploaded[b], 0));
+    // a pinned caller buffer is visible to the GPU at its mapped address (UVA)
+    const float* mapped = nullptr;
+    {
+      cudaPointerAttributes pa;
+      if (cudaPointerGetAttributes(&pa, depth) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) mapped = static_cast<const float*>(pa.devicePointer);
+      cudaGetLastError();
+    }
     e->cur_depth = e->d_depth[b];
     e->cur_rgb = (rgb && e->S.use_color) ? e->d_rgb[b] : nullptr;
     e->buf_used[b] = true;
@@ -436,7 +447,7 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
     setup_frame(e, c2w);
     const int keep = e->S.use_color;   // colour only when the caller supplied an image
     e->S.use_color = e->cur_rgb ? keep : 0;
-    rc = enqueue_stages(e, true, with_rgb ? e->ev_rgb[b] : nullptr);
+    rc = enqueue_stages(e, true, e->ev_uploaded[b], with_rgb ? e->ev_rgb[b] : nullptr, mapped);
     e->S.use_color = keep;
     if (rc != VH_OK) return rc;
     CK(cudaEventRecord(e->ev_consumed[b], e->stream));
@@ -447,7 +458,7 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
     setup_frame(e, c2w);
     const int keep = e->S.use_color;
     e->S.use_color = e->cur_rgb ? keep : 0;
-    rc = enqueue_stages(e, true, nullptr);
+    rc = enqueue_stages(e, true, nullptr, nullptr, nullptr);
     e->S.use_color = keep;
     if (rc != VH_OK) return rc;
   }

@@ -72,7 +72,7 @@ void shard_release(vh_engine* e);               // vh_shard.cu: called by vh_des
 int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out, unsigned long long total, vh_triangle** d_keep);   // ordered soup of mb's blocks
 int weld_on_device(vh_engine* e, const vh_triangle* d_soup, unsigned long long T, std::vector<vh_vertex>& verts, std::vector<int32_t>& faces);   // vh_weld.cu
 extern "C" {
-int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t rgb_ready);
+int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEvent_t rgb_ready, const float* host_depth_mapped);
 int enqueue_readback(vh_engine* e);
 int finish_sync(vh_engine* e);
 int make_room(vh_engine* e);
