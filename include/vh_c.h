@@ -109,6 +109,9 @@ VH_API int vh_integrate(vh_engine* e, const float* depth, const uint8_t* rgb, co
 /* Same work, asynchronous on the engine's stream: returns after enqueueing. The host buffers must stay
  * untouched until vh_sync() (or vh_wait_uploads()) returns. Uploads of frame k+1 overlap kernels of frame k. */
 VH_API int vh_integrate_async(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w);
+/* Depth as raw u16 samples (the reference's depth PNGs, SaveFrame.cpp:174-180): metres = (float)sample * depth_scale,
+ * computed on the GPU exactly as frameLoad's convertTo + scale does; half the upload bytes of the f32 form. */
+VH_API int vh_integrate_u16_async(vh_engine* e, const uint16_t* depth_u16, double depth_scale, const uint8_t* rgb, const float* c2w);
 VH_API int vh_wait_uploads(vh_engine* e);
 VH_API int vh_sync(vh_engine* e);
 /* Inputs already resident in HBM (device pointers on the engine's device); c2w stays a host pointer. */

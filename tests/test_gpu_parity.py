@@ -243,6 +243,28 @@ def test_pinned_host_frames_equal_pageable(vh, synth):
         L.vh_host_free(pd); L.vh_host_free(pc)
 
 
+def test_u16_depth_ingestion_equals_host_conversion(vh, synth):
+    """u16-millimetre depth converted on the GPU gives the map of the host conversion frameLoad performs
+    (convertTo(CV_32FC1) then *= 0.001, /root/reference/src/SaveFrame.cpp:174-180)."""
+    sc = synth.Scene(width=320, height=240, room=(5.0, 4.0, 2.6), n_frames=30, color=True, holes=0.02)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.02, trunc=0.1, max_depth=3.5)
+    with vh.TsdfEngine(engine_params(vh, sc, case)) as a, vh.TsdfEngine(engine_params(vh, sc, case)) as b:
+        keep = []
+        for i in range(5):
+            d, rgb, c2w = sc.frame(i)
+            mm = np.ascontiguousarray(np.round(d.astype(np.float64) * 1000.0).astype(np.uint16))
+            host = (mm.astype(np.float32).astype(np.float64) * 0.001).astype(np.float32)
+            a.processFrame(host, rgb, c2w)
+            keep.append((mm, rgb, c2w))
+            b.integrate_u16_async(mm, 0.001, rgb, c2w)
+        b.sync()
+        keys = sort_keys(a.allocated_keys())
+        assert len(keys) > 0 and np.array_equal(keys, sort_keys(b.allocated_keys()))
+        for x, y in zip(a.download_blocks(keys), b.download_blocks(keys)):
+            assert np.array_equal(x, y)
+        assert np.array_equal(a.triangles()[0], b.triangles()[0])
+
+
 def test_empty_frames_and_errors(vh, synth):
     case = CASES["g8_color_holes"]
     sc = synth.Scene(**case["scene"])

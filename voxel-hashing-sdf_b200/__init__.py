@@ -28,7 +28,7 @@ STATUS = {0: "VH_OK", 1: "VH_ERR_INVALID", 2: "VH_ERR_NO_DEVICE", 3: "VH_ERR_CUD
 # every symbol include/vh_c.h declares (checked by tests/test_abi.py against the header and the .so)
 ABI_SYMBOLS = [
     "vh_last_error", "vh_version", "vh_default_params", "vh_create", "vh_destroy", "vh_reset",
-    "vh_integrate", "vh_integrate_async", "vh_wait_uploads", "vh_sync", "vh_integrate_device",
+    "vh_integrate", "vh_integrate_async", "vh_integrate_u16_async", "vh_wait_uploads", "vh_sync", "vh_integrate_device",
     "vh_upload_frame", "vh_stage_allocate", "vh_stage_integrate", "vh_stage_marching_cubes", "vh_set_visible",
     "vh_get_stats", "vh_stream", "vh_visible_keys", "vh_allocated_keys", "vh_download_blocks", "vh_voxel_checksum",
     "vh_extract_mesh", "vh_save_ply", "vh_save_ply_binary", "vh_weld_mesh", "vh_host_alloc", "vh_host_free",
@@ -100,6 +100,7 @@ def load_library():
         getattr(L, name).argtypes = [vp]
     for name in ("vh_integrate", "vh_integrate_async", "vh_integrate_device"):
         getattr(L, name).argtypes = [vp, vp, vp, vp]
+    L.vh_integrate_u16_async.argtypes = [vp, vp, C.c_double, vp, vp]
     L.vh_upload_frame.argtypes = [vp, vp, vp]
     L.vh_stage_allocate.argtypes = [vp, vp, vp]
     L.vh_stage_integrate.argtypes = [vp, vp, vp]
@@ -220,6 +221,11 @@ class TsdfEngine:
     def integrate_async(self, depth, rgb, c2w):
         """Enqueue one frame; buffers (numpy arrays or raw pinned addresses) must stay alive until sync()."""
         _check(self.L.vh_integrate_async(self.h, _ptr(depth), _ptr(rgb), _ptr(c2w)))
+
+    def integrate_u16_async(self, depth_u16, depth_scale, rgb, c2w):
+        """u16 depth samples (e.g. millimetres with depth_scale 0.001), converted on the GPU; buffers must stay alive until sync()"""
+        self._keep = (depth_u16, rgb, c2w)
+        _check(self.L.vh_integrate_u16_async(self.h, _ptr(depth_u16), float(depth_scale), _ptr(rgb), _ptr(c2w)))
 
     def integrate_device(self, d_depth: int, d_rgb, c2w):
         _check(self.L.vh_integrate_device(self.h, d_depth, d_rgb, _ptr(c2w)))

@@ -97,7 +97,7 @@ static int free_engine(vh_engine* e) {
   cudaFree(D.tri_offset); cudaFree(D.tri_count);
   cudaFree(e->d_full_list); cudaFree(e->d_full_count); cudaFree(e->d_full_off); cudaFree(e->d_full_cnt); cudaFree(e->d_keys_tmp);
   for (int i = 0; i < 2; i++) {
-    cudaFree(e->d_depth[i]); cudaFree(e->d_rgb[i]); cudaFree(e->d_px[i]);
+    cudaFree(e->d_depth[i]); cudaFree(e->d_depth16[i]); cudaFree(e->d_rgb[i]); cudaFree(e->d_px[i]);
     if (e->ev_uploaded[i]) cudaEventDestroy(e->ev_uploaded[i]);
     if (e->ev_rgb[i]) cudaEventDestroy(e->ev_rgb[i]);
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
@@ -416,8 +416,16 @@ int make_room(vh_engine* e) {
   return compact_arena(e, per_frame * 2);
 }
 
-static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w, bool host_inputs) {
-  if (!e || !depth || !c2w) return fail(VH_ERR_INVALID, "null argument");
+// u16 depth (PNG millimetres, SaveFrame.cpp:174-180) -> f32 metres on the device: convertTo(CV_32FC1) then *= scale,
+// i.e. the float value of the sample times the double scale, rounded once to float
+__global__ void depth_u16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int n, double scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __double2float_rn(__dmul_rn((double)(float)in[i], scale));
+}
+
+static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w, bool host_inputs,
+                            const uint16_t* depth_u16 = nullptr, double depth_scale = 0.0) {
+  if (!e || (!depth && !depth_u16) || !c2w) return fail(VH_ERR_INVALID, "null argument");
   CK(cudaSetDevice(e->P.device));
   int rc = make_room(e);
   if (rc != VH_OK) return rc;
@@ -426,7 +434,13 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
   if (host_inputs) {
     const int b = e->ring & 1; e->ring++;
     if (e->buf_used[b]) CK(cudaStreamWaitEvent(e->upload, e->ev_consumed[b], 0));     // previous reader of this buffer is done
-    CK(cudaMemcpyAsync(e->d_depth[b], depth, npx * sizeof(float), cudaMemcpyHostToDevice, e->upload));
+    if (depth_u16) {          // half the bytes over PCIe; converted on the upload stream, so it overlaps the previous frame too
+      if (!e->d_depth16[b]) CK(cudaMalloc((void**)&e->d_depth16[b], npx * sizeof(uint16_t)));
+      CK(cudaMemcpyAsync(e->d_depth16[b], depth_u16, npx * sizeof(uint16_t), cudaMemcpyHostToDevice, e->upload));
+      depth_u16_to_f32_kernel<<<(int)((npx + 255) / 256), 256, 0, e->upload>>>(e->d_depth16[b], e->d_depth[b], (int)npx, depth_scale);
+    } else {
+      CK(cudaMemcpyAsync(e->d_depth[b], depth, npx * sizeof(float), cudaMemcpyHostToDevice, e->upload));
+    }
     CK(cudaEventRecord(e->ev_uploaded[b], e->upload));
     const bool with_rgb = rgb && e->S.use_color;
     if (with_rgb) {
@@ -437,7 +451,7 @@ static int integrate_common(vh_engine* e, const float* depth, const uint8_t* rgb
     const float* mapped = nullptr;
     {
       cudaPointerAttributes pa;
-      if (cudaPointerGetAttributes(&pa, depth) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) mapped = static_cast<const float*>(pa.devicePointer);
+      if (depth && cudaPointerGetAttributes(&pa, depth) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) mapped = static_cast<const float*>(pa.devicePointer);
       cudaGetLastError();
     }
     e->cur_depth = e->d_depth[b];
@@ -476,6 +490,14 @@ int vh_integrate_device(vh_engine* e, const float* d_depth, const uint8_t* d_rgb
   if (!e) return fail(VH_ERR_INVALID, "null engine");
   std::lock_guard<std::mutex> lk(e->mtx);
   return integrate_common(e, d_depth, d_rgb, c2w, false);
+}
+
+// depth as the u16 samples of the reference's depth PNGs (millimetres when depth_scale = 0.001, the factor frameLoad
+// applies, SaveFrame.cpp:180): uploaded as 2 bytes per pixel and converted on the GPU. Asynchronous like vh_integrate_async.
+int vh_integrate_u16_async(vh_engine* e, const uint16_t* depth_u16, double depth_scale, const uint8_t* rgb, const float* c2w) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  return integrate_common(e, nullptr, rgb, c2w, true, depth_u16, depth_scale);
 }
 
 int vh_wait_uploads(vh_engine* e) {

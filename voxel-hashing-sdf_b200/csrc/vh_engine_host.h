@@ -29,6 +29,7 @@ struct vh_engine {
   uint32_t capacity = 0;
   cudaStream_t stream = nullptr, upload = nullptr;
   float* d_depth[2] = {nullptr, nullptr};
+  uint16_t* d_depth16[2] = {nullptr, nullptr};   // staging of u16 depth frames (vh_integrate_u16_async), allocated on first use
   uint8_t* d_rgb[2] = {nullptr, nullptr};
   uint2* d_px[2] = {nullptr, nullptr};     // packed {depth, rgb} records the integrate kernel reads
   int px_ring = 0;
