@@ -13,6 +13,9 @@ started from an empty map.
   e2e     frames/s through the reference-facing call (vh_integrate == GpuTsdfGenerator::processFrame): pinned HOST
           buffers, the H2D copies of depth+rgb and the D2H read of the frame's counters inside the timed region,
           synchronous per frame like the reference
+          e2e.async_value / e2e.u16_async: the non-blocking calls (vh_integrate_async, vh_integrate_u16_async) from the same
+          pinned buffers; u16 = the reference loader's millimetre samples, converted on the GPU
+  export  after the last frame: ordered gather + GPU vertex welding + one D2H, and the binary PLY
   roofline  the integrate kernel: algorithmic bytes (16 B x voxel updates + 4 W H + 12 B x visible blocks, + colour
           8 B x updates + 3 W H) / its CUDA-event time, vs the measured HBM copy peak
   cpu_baseline  the CPU oracle (port of the reference's algorithm, oracle/vh_oracle.c) on this box's host cores,
@@ -31,6 +34,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -39,6 +43,7 @@ sys.path.insert(0, ROOT)
 FRAMES_PER_STEP = 50
 METRIC = "depth_frames_per_sec_640x480_5mm"
 UNIT = "frames/s"
+SHARDED_TIMEOUT_S = 300     # bench.py --gpus N>1: upper bound for the optional sharded-map section
 
 
 def parse():
@@ -281,6 +286,34 @@ def run_ours(args):
     barrier()
     ms_e2e_async = max_over_ranks(max(e0.elapsed_time(e1), wall_async))
 
+    # ---- frame ingestion as the reference's loader delivers it (u16 millimetres, SaveFrame.cpp:174-180): 2 bytes per depth
+    #      sample over PCIe, converted on the GPU (vh_integrate_u16_async); measured for SURVEY.md 8(f) row 2 ----
+    u16 = None
+    try:
+        if world > 1:
+            raise RuntimeError("measured at --gpus 1 only")
+        h_depth16 = (h_depth * 1000.0).round().to(torch.int16).pin_memory()      # bit pattern of the u16 sample (< 32768 mm)
+        eng.reset()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in frames_of(n_timed):
+            rc = L.vh_integrate_u16_async(hp, dptr(h_depth16, i), 0.001, rgb_host(i), poses[i].ctypes.data)
+            if rc != 0:
+                raise vh.VhError(rc, L.vh_last_error().decode())
+        eng.sync()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall_u16 = (time.perf_counter() - t0) * 1000.0
+        barrier()
+        ms_u16 = max_over_ranks(max(e0.elapsed_time(e1), wall_u16))
+        u16 = {"value": sum_over_ranks(float(n_timed)) / (ms_u16 / 1000.0),
+               "h2d_bytes_per_step": (W * H * 2 + (W * H * 3 if color else 0) + 64) * FRAMES_PER_STEP,
+               "call": "vh_integrate_u16_async per frame (pinned u16-millimetre depth + rgb, converted on the GPU) + one vh_sync"}
+        del h_depth16
+    except Exception as ex:      # never lose the headline to an auxiliary measurement
+        u16 = {"error": f"{type(ex).__name__}: {ex}"}
+
     # ---- per-kernel profile pass (untimed for the headline): CUDA-event time of every stage of every frame ----
     eng.reset()
     acc = dict(alloc=0.0, integrate=0.0, mc=0.0, upload=0.0, updates=0, visible=0, tris=0, culled=0)
@@ -292,6 +325,31 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     st_last = eng.stats()
     allocated = st_last.allocated_blocks
+
+    # ---- mesh export of the finished map: persistent per-block meshes gathered in tsdf2mesh order,
+    #      welded on the GPU, copied out once; then the binary PLY of the same mesh. Rank 0 only, outside every timed region. ----
+    export = None
+    if rank == 0 and not args.no_mc:
+        try:
+            import ctypes as C
+            nv, nf = C.c_uint64(), C.c_uint64()
+            t0 = time.perf_counter()
+            rc = L.vh_weld_mesh(hp, vh.VH_MESH_REF_PERSISTENT, None, 0, C.byref(nv), None, 0, C.byref(nf))
+            t_weld = time.perf_counter() - t0
+            if rc != 0:
+                raise vh.VhError(rc, L.vh_last_error().decode())
+            ply = os.path.join(tempfile.gettempdir(), f"vh_bench_{os.getpid()}.ply")
+            t0 = time.perf_counter()
+            eng.save_ply_binary(ply)
+            t_ply = time.perf_counter() - t0
+            ply_bytes = os.path.getsize(ply)
+            os.remove(ply)
+            export = {"faces": int(nf.value), "vertices": int(nv.value), "ms_gather_weld_copy": 1000.0 * t_weld,
+                      "faces_per_sec": nf.value / t_weld if t_weld > 0 else None,
+                      "ms_save_ply_binary": 1000.0 * t_ply, "ply_bytes": ply_bytes,
+                      "call": "vh_weld_mesh (counts only: ordered gather + GPU weld + one D2H) and vh_save_ply_binary after the last frame"}
+        except Exception as ex:
+            export = {"error": f"{type(ex).__name__}: {ex}"}
 
     total_frames = sum_over_ranks(float(n_timed))
     value = total_frames / (ms_value / 1000.0)
@@ -325,7 +383,8 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * FRAMES_PER_STEP, "d2h_bytes_per_step": d2h * FRAMES_PER_STEP,
                 "call": "vh_integrate (GpuTsdfGenerator::processFrame drop-in), pinned host depth+rgb, synchronous per frame",
                 "async_value": total_frames / (ms_e2e_async / 1000.0),
-                "async_call": "vh_integrate_async per frame from the same pinned host buffers + one vh_sync: uploads overlap kernels"},
+                "async_call": "vh_integrate_async per frame from the same pinned host buffers + one vh_sync: uploads overlap kernels",
+                "u16_async": u16},
         "gpu_launches": (5 if not args.no_mc else 3) * n_timed,      # pack, allocate, integrate (+ mc_filter, mc_mesh) per frame
         "voxel_updates_per_sec": sum_over_ranks(float(acc["updates"])) / (ms_value / 1000.0),
         "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "blocks_discarded_whole_by_integrate": acc["culled"] / n_timed,
@@ -338,10 +397,26 @@ def run_ours(args):
         "roofline_mc": {"kernel": "vh::mc_filter_kernel + vh::mc_mesh_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
                         "peak": peak, "unit": "GB/s", "algorithmic_bytes_per_launch": bytes_mc, "avg_launch_ms": ms_mc},
         "clocks": clocks,
+        "export": export,
     }
     if world > 1:
-        line["sharded"] = run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, poses, n_timed, n_frames, dist, torch)
+        # The sharded-map section is an extra on top of the contract's line: if a rank stalls in it (dead peer, NCCL
+        # trouble) every rank gives up after SHARDED_TIMEOUT_S and rank 0 still prints the headline measured above.
+        def give_up():
+            if rank == 0:
+                line["sharded"] = {"error": f"sharded-map section did not finish within {SHARDED_TIMEOUT_S} s; the numbers above were measured before it"}
+                line["cpu_baseline"] = None
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(SHARDED_TIMEOUT_S, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            line["sharded"] = run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, poses, n_timed, n_frames, dist, torch)
+        except Exception as ex:      # the peers may be waiting in a collective: the watchdog ends them
+            line["sharded"] = {"error": f"{type(ex).__name__}: {ex}"}
         dist.barrier()
+        dog.cancel()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             fps, dt, threads, n = cpu_reference_run(args, args.cpu_frames, 1, args.cpu_frames, 0)
