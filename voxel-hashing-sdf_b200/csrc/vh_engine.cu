@@ -245,6 +245,11 @@ int vh_create(const vh_params* p, vh_engine** out) {
          cudaEventCreateWithFlags(&e->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
   if (!ok) { free_engine(e); return fail(VH_ERR_CUDA, "CUDA Error: stream/event creation failed"); }
+  {   // tuning knob, off by default: publish the status block from a kernel instead of a D2H copy (see publish_status_kernel)
+    const char* v = getenv("VH_STATUS_PUBLISH");
+    void* dp = nullptr;
+    if (v && v[0] == '1') { if (cudaHostGetDevicePointer(&dp, e->h_block, 0) == cudaSuccess) e->h_block_dev = static_cast<DeviceStatus*>(dp); else cudaGetLastError(); }
+  }
   upload_mc_tables();
   int rc = reset_map(e);
   if (rc != VH_OK) { free_engine(e); return rc; }
@@ -353,9 +358,29 @@ int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEve
   return VH_OK;
 }
 
+// Experimental route of the status block (VH_STATUS_PUBLISH=1, off by default): one warp stores
+// the 128-byte block into the mapped pinned host block instead of a D2H copy node, so that the frame ends without a
+// kernel -> copy engine -> kernel hand-off and never queues behind the next frame's upload. Word 0 holds the frame stamp
+// the host polls without a sync (make_room); it is stored last, after a system-scope fence.
+__global__ void publish_status_kernel(const DeviceStatus* __restrict__ src, DeviceStatus* dst_mapped) {
+  static_assert(sizeof(DeviceStatus) == 128, "one 8-byte word per lane of half a warp");
+  const int lane = threadIdx.x;
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+  volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(dst_mapped);
+  unsigned long long v = 0;
+  if (lane < 16) v = __ldcg(s + lane);
+  if (lane > 0 && lane < 16) d[lane] = v;
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) { d[0] = v; __threadfence_system(); }
+}
+
 int enqueue_readback(vh_engine* e) {
-  DeviceView& D = e->D;
-  (void)D;
+  if (e->h_block_dev) {
+    publish_status_kernel<<<1, 32, 0, e->stream>>>(e->d_status, e->h_block_dev);
+    CK(cudaGetLastError());
+    return VH_OK;
+  }
   CK(cudaMemcpyAsync(e->h_block, e->d_status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, e->stream));
   return VH_OK;
 }

@@ -42,6 +42,7 @@ struct vh_engine {
   // pinned read-back block: counters of the last frame + flags
   typedef DeviceStatus HostBlock;
   HostBlock* h_block = nullptr;
+  DeviceStatus* h_block_dev = nullptr;  // device-side address of h_block when the status is published by a kernel (VH_STATUS_PUBLISH=1)
   DeviceStatus* d_status = nullptr;     // counters, error flags, heap counter, arena top: one block, one read-back copy
   uint64_t frames = 0, updates_total = 0;
   uint64_t max_tris_per_frame = 0, known_arena_top = 0;
