@@ -1,0 +1,86 @@
+"""ctypes binding of tests/emu/libvh_emu.so: the engine's kernel sources executed on the CPU (test infrastructure).
+
+Only tests import this. The product (voxel-hashing-sdf_b200/, include/) never does: the engine has no CPU path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libvh_emu.so")
+
+
+class IntegrateIO(C.Structure):
+    _fields_ = [("W", C.c_int), ("H", C.c_int),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("max_depth", C.c_float),
+                ("vox_size", C.c_float), ("trunc", C.c_float),
+                ("use_color", C.c_int), ("cull", C.c_int), ("two_steps", C.c_int), ("verify", C.c_int), ("exact_color", C.c_int),
+                ("ctas", C.c_int), ("variant", C.c_int),
+                ("weight_bound", C.c_uint), ("frame", C.c_uint), ("rcp_seed", C.c_uint),
+                ("c2w", C.c_void_p), ("depth", C.c_void_p), ("rgb", C.c_void_p),
+                ("n_visible", C.c_int), ("keys_xyz", C.c_void_p), ("slots", C.c_void_p),
+                ("sdf", C.c_void_p), ("wgt", C.c_void_p), ("rgb4", C.c_void_p), ("neg_count", C.c_void_p),
+                ("voxel_updates", C.c_ulonglong), ("culled", C.c_ulonglong), ("mismatch", C.c_ulonglong), ("collectives", C.c_ulonglong),
+                ("engine_error", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-s", "-B", "-C", HERE, "libvh_emu.so"])   # always rebuilt: it mirrors the kernel sources of the moment
+        _lib = C.CDLL(LIB)
+        _lib.emu_integrate.argtypes = [C.POINTER(IntegrateIO)]
+        _lib.emu_integrate.restype = C.c_int
+    return _lib
+
+
+class EmuMap:
+    """Voxel planes + key -> slot dictionary driven by the emulated integrate kernel (the visible list comes from outside)."""
+
+    def __init__(self, scene, vox_size, trunc, max_depth, pool_blocks, color):
+        self.sc, self.vox, self.trunc, self.maxd, self.color = scene, vox_size, trunc, max_depth, color
+        self.sdf = np.zeros(pool_blocks * 512, np.float32)
+        self.wgt = np.zeros(pool_blocks * 512, np.float32)
+        self.rgb4 = np.zeros(pool_blocks * 512 * 4, np.uint8)
+        self.neg = np.zeros(pool_blocks, np.int32)
+        self.slot_of = {}
+        self.frames = 0
+
+    def slots_for(self, keys):
+        out = np.empty(len(keys), np.int32)
+        for i, k in enumerate(map(tuple, np.asarray(keys).tolist())):
+            if k not in self.slot_of:
+                self.slot_of[k] = len(self.slot_of)
+            out[i] = self.slot_of[k]
+        assert len(self.slot_of) <= len(self.neg), "emulated pool too small"
+        return out
+
+    def integrate(self, keys, depth, rgb, c2w, *, cull=1, two_steps=0, verify=0, exact_color=0, ctas=2, variant=0, rcp_seed=1):
+        self.frames += 1
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        slots = self.slots_for(keys)
+        depth = np.ascontiguousarray(depth, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        c2w = np.ascontiguousarray(c2w, np.float32)
+        sc = self.sc
+        io = IntegrateIO(W=sc.width, H=sc.height, fx=sc.fx, fy=sc.fy, cx=sc.cx, cy=sc.cy, max_depth=self.maxd, vox_size=self.vox,
+                         trunc=self.trunc, use_color=int(self.color), cull=cull, two_steps=two_steps, verify=verify,
+                         exact_color=exact_color, ctas=ctas, variant=variant, weight_bound=self.frames, frame=self.frames, rcp_seed=rcp_seed,
+                         c2w=c2w.ctypes.data, depth=depth.ctypes.data, rgb=rgb.ctypes.data, n_visible=len(keys),
+                         keys_xyz=keys.ctypes.data, slots=slots.ctypes.data, sdf=self.sdf.ctypes.data, wgt=self.wgt.ctypes.data,
+                         rgb4=self.rgb4.ctypes.data, neg_count=self.neg.ctypes.data)
+        rc = lib().emu_integrate(C.byref(io))
+        assert rc == 0, f"emu_integrate failed: {rc}"
+        return io
+
+    def blocks(self, keys):
+        slots = self.slots_for(np.asarray(keys).reshape(-1, 3))
+        s = self.sdf.reshape(-1, 512)[slots]
+        w = self.wgt.reshape(-1, 512)[slots]
+        c = self.rgb4.reshape(-1, 512, 4)[slots]
+        return s, w, c, slots

@@ -1,0 +1,93 @@
+// tests/emu/emu_kernels.cpp — runs the engine's integrate/pack kernels (the product's own source, included as text) on
+// the CPU through tests/emu/cuda_runtime.h. TEST INFRASTRUCTURE ONLY: built by tests/emu/Makefile into
+// tests/emu/libvh_emu.so and loaded by tests/test_emu_integrate.py; libvhsdf.so never links or loads it.
+#include <cuda_runtime.h>
+#include "emu_runtime.h"
+
+#include "../../voxel-hashing-sdf_b200/csrc/vh_integrate.cu"
+
+namespace {
+
+struct IntegrateArgs { vh::StaticParams S; vh::FrameParams F; const uint2* px; vh::DeviceView D; int variant; };
+
+template <bool C, bool V, bool T, bool Q, bool CULL>
+void run_variant(void* p) {
+  IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
+  vh::integrate_kernel<C, V, 4, T, Q, true, CULL>(a->S, a->F, a->px, a->D);
+}
+
+struct PackArgs { const float* depth; const uint8_t* rgb; uint2* out; int W, H; float* tile_max; int* sched; vh::FrameCounters* counters; uint32_t frame; };
+void run_pack(void* p) {
+  PackArgs* a = static_cast<PackArgs*>(p);
+  vh::pack_frame_kernel(a->depth, a->rgb, a->out, a->W, a->H, a->tile_max, a->sched, a->counters, a->frame, 0);
+}
+
+}  // namespace
+
+extern "C" {
+
+struct emu_integrate_io {
+  int W, H;
+  float fx, fy, cx, cy, max_depth, vox_size, trunc;
+  int use_color, cull, two_steps, verify, exact_color, ctas, variant;   // ctas: emulated grid size in 256-thread CTAs; variant: kernel revision (0 = shipped default)
+  unsigned weight_bound, frame, rcp_seed;
+  const float* c2w;              // [16]
+  const float* depth;            // [H*W]
+  const uint8_t* rgb;            // [H*W*3] or null
+  int n_visible;
+  const int* keys_xyz;           // [n][3] block coordinates of the frame's visible list
+  const int* slots;              // [n] pool slot of each
+  float* sdf; float* wgt; uint8_t* rgb4; int* neg_count;   // planes: [pool*512] f32, f32, u8x4; [pool]
+  unsigned long long voxel_updates, culled, mismatch, collectives;   // out
+  int engine_error;              // out
+};
+
+int emu_integrate(emu_integrate_io* io) {
+  using namespace vh;
+  emu::g_rcp_seed = io->rcp_seed;
+  StaticParams S; memset(&S, 0, sizeof(S));
+  S.W = io->W; S.H = io->H; S.fx = io->fx; S.fy = io->fy; S.cx = io->cx; S.cy = io->cy; S.max_depth = io->max_depth;
+  S.vox_size = io->vox_size; S.trunc = io->trunc; S.use_color = io->use_color;
+  S.round_eps = 7.5e-7f * (float)std::max(io->W, io->H) + 2e-5f;    // vh_create, csrc/vh_engine.cu
+  S.verify = io->verify; S.weight_bound = io->weight_bound; S.integrate_cull = io->cull; S.integrate_two_steps = io->two_steps;
+  FrameParams F; memset(&F, 0, sizeof(F));
+  memcpy(F.c2w, io->c2w, sizeof(F.c2w)); F.frame = io->frame;
+
+  const int n = io->n_visible;
+  std::vector<u64> keys(std::max(n, 1));
+  std::vector<int> visible(std::max(n, 1));
+  for (int i = 0; i < n; i++) { keys[i] = pack_key(io->keys_xyz[3 * i], io->keys_xyz[3 * i + 1], io->keys_xyz[3 * i + 2]); visible[i] = i; }
+  const int tiles = ((io->W + 15) / 16) * ((io->H + 15) / 16);
+  std::vector<float> tile_max(tiles, -1.0f);
+  std::vector<int> sched(NSCHED * 32, 12345);    // pack_frame_kernel must zero the counters it owns
+  std::vector<uint2> px((size_t)io->W * io->H);
+  FrameCounters counters; memset(&counters, 0xAB, sizeof(counters));
+  int engine_error = 0; unsigned long long updates_total = 0;
+
+  PackArgs pa{io->depth, io->use_color ? io->rgb : nullptr, px.data(), io->W, io->H, tile_max.data(), sched.data(), &counters, io->frame};
+  emu::run_grid(dim3((io->W + 15) / 16, (io->H + 15) / 16), dim3(16, 16), run_pack, &pa);
+  if (counters.visible_count != 0 || counters.frame != io->frame || counters.voxel_updates != 0) return -2;
+  counters.visible_count = n;     // the allocation pass would have counted the list
+
+  DeviceView D; memset(&D, 0, sizeof(D));
+  D.map.keys = keys.data(); D.map.slots = const_cast<int*>(io->slots);
+  D.sdf = io->sdf; D.wgt = io->wgt; D.rgb = reinterpret_cast<uchar4*>(io->rgb4); D.neg_count = io->neg_count;
+  D.sched = sched.data(); D.tile_max = tile_max.data(); D.visible = visible.data(); D.list_cap = std::max(n, 1);
+  D.counters = &counters; D.engine_error = &engine_error; D.updates_total = &updates_total;
+
+  IntegrateArgs ia{S, F, px.data(), D, 0};
+  const bool color = io->use_color != 0, fast = !io->exact_color && S.weight_bound <= 4096u;
+  void (*entry)(void*) = nullptr;
+#define PICK(C, V, T, Q) (io->cull ? run_variant<C, V, T, Q, true> : run_variant<C, V, T, Q, false>)
+  if (io->verify) entry = !color ? PICK(false, true, false, false) : fast ? PICK(true, true, false, true) : PICK(true, true, false, false);
+  else if (io->two_steps) entry = !color ? PICK(false, false, true, false) : fast ? PICK(true, false, true, true) : PICK(true, false, true, false);
+  else entry = !color ? PICK(false, false, false, false) : fast ? PICK(true, false, false, true) : PICK(true, false, false, false);
+#undef PICK
+  emu::g_collectives = 0;
+  emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(INT_THREADS), entry, &ia);
+  io->voxel_updates = counters.voxel_updates; io->culled = counters.pad[1]; io->mismatch = counters.pad[0];
+  io->collectives = emu::g_collectives; io->engine_error = engine_error;
+  return updates_total == counters.voxel_updates ? 0 : -3;
+}
+
+}  // extern "C"

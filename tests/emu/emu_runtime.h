@@ -1,0 +1,61 @@
+// tests/emu/emu_runtime.h — the fibre scheduler behind tests/emu/cuda_runtime.h. TEST INFRASTRUCTURE ONLY.
+// Include once, in the harness's translation unit.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace emu {
+
+Cta* g_cta = nullptr;
+unsigned long long g_collectives = 0, g_events = 0;
+unsigned g_rcp_seed = 12345u;
+
+void trampoline() {
+  Cta* c = g_cta;
+  c->entry(c->arg);
+  c->cur->done = true;
+  swapcontext(&c->cur->ctx, &c->sched);
+}
+
+void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg) {
+  const int nthreads = (int)(block.x * block.y * block.z);
+  const size_t stack_bytes = 256 << 10;
+  Cta cta;
+  cta.fibres.resize(nthreads);
+  for (auto& f : cta.fibres) f.stack = (char*)malloc(stack_bytes);
+  cta.bdim = block; cta.gdim = grid; cta.entry = entry; cta.arg = arg;
+  Cta* const outer = g_cta;
+  g_cta = &cta;
+  for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
+    cta.bid = uint3{bx, by, bz};
+    cta.warps.assign((nthreads + 31) / 32, Group());
+    for (size_t w = 0; w < cta.warps.size(); w++) cta.warps[w].size = std::min(32, nthreads - (int)w * 32);
+    cta.all = Group(); cta.all.size = nthreads;
+    for (int t = 0; t < nthreads; t++) {
+      Fibre& f = cta.fibres[t];
+      f.done = false; f.warp_parity = 0;
+      f.tid = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = nullptr;
+      makecontext(&f.ctx, (void (*)())trampoline, 0);
+    }
+    int live = nthreads;
+    while (live > 0) {
+      const unsigned long long events_before = g_events;
+      for (int t = 0; t < nthreads; t++) {
+        Fibre& f = cta.fibres[t];
+        if (f.done) continue;
+        cta.cur = &f;
+        swapcontext(&cta.sched, &f.ctx);
+        if (f.done) { live--; g_events++; }
+      }
+      if (g_events == events_before) {   // a whole round in which no barrier opened and no thread finished
+        fprintf(stderr, "emu: deadlock — %d threads wait at a collective their warp/CTA cannot complete (divergent collective?)\n", live);
+        abort();
+      }
+    }
+  }
+  g_cta = outer;
+  for (auto& f : cta.fibres) free(f.stack);
+}
+
+}  // namespace emu
