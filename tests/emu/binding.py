@@ -22,7 +22,7 @@ class IntegrateIO(C.Structure):
                 ("c2w", C.c_void_p), ("depth", C.c_void_p), ("rgb", C.c_void_p),
                 ("n_visible", C.c_int), ("keys_xyz", C.c_void_p), ("slots", C.c_void_p),
                 ("sdf", C.c_void_p), ("wgt", C.c_void_p), ("rgb4", C.c_void_p), ("neg_count", C.c_void_p),
-                ("voxel_updates", C.c_ulonglong), ("culled", C.c_ulonglong), ("mismatch", C.c_ulonglong), ("collectives", C.c_ulonglong),
+                ("voxel_updates", C.c_ulonglong), ("culled", C.c_ulonglong), ("mismatch", C.c_ulonglong), ("collectives", C.c_ulonglong), ("slow_steps", C.c_ulonglong),
                 ("engine_error", C.c_int)]
 
 

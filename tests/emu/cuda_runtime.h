@@ -31,6 +31,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __constant__ static
+#define __grid_constant__
 #define __CUDACC__ 1
 #define VH_HOST_EMU 1
 

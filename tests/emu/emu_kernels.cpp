@@ -16,6 +16,12 @@ void run_variant(void* p) {
   vh::integrate_kernel<C, V, 4, T, Q, true, CULL>(a->S, a->F, a->px, a->D);
 }
 
+template <bool C, bool V, bool DL, bool CULL>
+void run_r1(void* p) {
+  IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
+  vh::integrate_kernel_r1<C, V, DL, CULL, 4>(a->S, a->F, a->px, a->D);
+}
+
 struct PackArgs { const float* depth; const uint8_t* rgb; uint2* out; int W, H; float* tile_max; int* sched; vh::FrameCounters* counters; uint32_t frame; };
 void run_pack(void* p) {
   PackArgs* a = static_cast<PackArgs*>(p);
@@ -38,7 +44,7 @@ struct emu_integrate_io {
   const int* keys_xyz;           // [n][3] block coordinates of the frame's visible list
   const int* slots;              // [n] pool slot of each
   float* sdf; float* wgt; uint8_t* rgb4; int* neg_count;   // planes: [pool*512] f32, f32, u8x4; [pool]
-  unsigned long long voxel_updates, culled, mismatch, collectives;   // out
+  unsigned long long voxel_updates, culled, mismatch, collectives, slow_steps;   // out
   int engine_error;              // out
 };
 
@@ -49,7 +55,7 @@ int emu_integrate(emu_integrate_io* io) {
   S.W = io->W; S.H = io->H; S.fx = io->fx; S.fy = io->fy; S.cx = io->cx; S.cy = io->cy; S.max_depth = io->max_depth;
   S.vox_size = io->vox_size; S.trunc = io->trunc; S.use_color = io->use_color;
   S.round_eps = 7.5e-7f * (float)std::max(io->W, io->H) + 2e-5f;    // vh_create, csrc/vh_engine.cu
-  S.verify = io->verify; S.weight_bound = io->weight_bound; S.integrate_cull = io->cull; S.integrate_two_steps = io->two_steps;
+  S.byte_bias = 0x4B000000u; S.verify = io->verify; S.weight_bound = io->weight_bound; S.integrate_cull = io->cull; S.integrate_two_steps = io->two_steps;
   FrameParams F; memset(&F, 0, sizeof(F));
   memcpy(F.c2w, io->c2w, sizeof(F.c2w)); F.frame = io->frame;
 
@@ -60,7 +66,7 @@ int emu_integrate(emu_integrate_io* io) {
   const int tiles = ((io->W + 15) / 16) * ((io->H + 15) / 16);
   std::vector<float> tile_max(tiles, -1.0f);
   std::vector<int> sched(NSCHED * 32, 12345);    // pack_frame_kernel must zero the counters it owns
-  std::vector<uint2> px((size_t)io->W * io->H);
+  std::vector<uint2> px((size_t)io->W * io->H + 1, make_uint2(0u, 0u));   // + the sentinel record (vh_create)
   FrameCounters counters; memset(&counters, 0xAB, sizeof(counters));
   int engine_error = 0; unsigned long long updates_total = 0;
 
@@ -83,10 +89,17 @@ int emu_integrate(emu_integrate_io* io) {
   else if (io->two_steps) entry = !color ? PICK(false, false, true, false) : fast ? PICK(true, false, true, true) : PICK(true, false, true, false);
   else entry = !color ? PICK(false, false, false, false) : fast ? PICK(true, false, false, true) : PICK(true, false, false, false);
 #undef PICK
+  if (io->variant == 1) {     // integrate_kernel_r1, dispatched like launch_integrate does
+    const bool delta = !io->exact_color && S.weight_bound <= 65536u;
+#define PICK1(C, V, DL) (io->cull ? run_r1<C, V, DL, true> : run_r1<C, V, DL, false>)
+    if (io->verify) entry = !color ? PICK1(false, true, false) : delta ? PICK1(true, true, true) : PICK1(true, true, false);
+    else entry = !color ? PICK1(false, false, false) : delta ? PICK1(true, false, true) : PICK1(true, false, false);
+#undef PICK1
+  }
   emu::g_collectives = 0;
   emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(INT_THREADS), entry, &ia);
   io->voxel_updates = counters.voxel_updates; io->culled = counters.pad[1]; io->mismatch = counters.pad[0];
-  io->collectives = emu::g_collectives; io->engine_error = engine_error;
+  io->collectives = emu::g_collectives; io->slow_steps = counters.pad[2]; io->engine_error = engine_error;
   return updates_total == counters.voxel_updates ? 0 : -3;
 }
 

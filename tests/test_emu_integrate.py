@@ -18,6 +18,7 @@ def run_case(ob, synth, *, scene_kw, vox, trunc, maxd=3.0, frames=3, color=True,
     m = EmuMap(sc, vox, trunc, maxd, pool_blocks=1 << 13, color=color)
     total_updates = total_culled = 0
     max_weight = 0.0
+    run_case.slow_steps = 0
     for i in range(frames):
         d, rgb, c2w = sc.frame(i)
         if mutate is not None:
@@ -32,6 +33,7 @@ def run_case(ob, synth, *, scene_kw, vox, trunc, maxd=3.0, frames=3, color=True,
         assert io.mismatch == 0
         total_updates += upd
         total_culled += io.culled
+        run_case.slow_steps += io.slow_steps
         allk = o.all_keys()
         so, wo, co, found = o.get_blocks(keys)
         se, we, ce, slots = m.blocks(keys)
@@ -50,32 +52,41 @@ def run_case(ob, synth, *, scene_kw, vox, trunc, maxd=3.0, frames=3, color=True,
 SMALL = dict(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=60, spheres=((2.8, 1.5, 1.0, 0.4),), color=True)
 
 
-def test_emulated_integrate_matches_oracle(ob, synth):
-    upd, culled = run_case(ob, synth, scene_kw=SMALL, vox=0.04, trunc=0.2)
+# kernel revisions: 0 = integrate_kernel (shipped default), 1 = integrate_kernel_r1 (VH_INTEGRATE_REV=1)
+REVS = [0, 1]
+
+
+@pytest.mark.parametrize("rev", REVS)
+def test_emulated_integrate_matches_oracle(ob, synth, rev):
+    upd, culled = run_case(ob, synth, scene_kw=SMALL, vox=0.04, trunc=0.2, variant=rev)
     assert upd > 20000
 
 
-def test_emulated_integrate_fine_voxels_discards_blocks(ob, synth):
+@pytest.mark.parametrize("rev", REVS)
+def test_emulated_integrate_fine_voxels_discards_blocks(ob, synth, rev):
     """small truncation band: most visible blocks lie behind the surface and the whole-block discard must drop them
     without changing a voxel; the same frames with the discard off give the same map."""
-    kw = dict(scene_kw=dict(SMALL, holes=0.02), vox=0.02, trunc=0.06, frames=2)
+    kw = dict(scene_kw=dict(SMALL, holes=0.02), vox=0.02, trunc=0.06, frames=2, variant=rev)
     upd, culled = run_case(ob, synth, **kw)
     assert culled > 0
     upd2, culled2 = run_case(ob, synth, cull=0, **kw)
     assert culled2 == 0 and upd2 == upd
 
 
-@pytest.mark.parametrize("kernel_kw", [dict(two_steps=1), dict(exact_color=1), dict(verify=1), dict(ctas=1)])
+@pytest.mark.parametrize("kernel_kw", [dict(two_steps=1), dict(exact_color=1), dict(verify=1), dict(ctas=1),
+                                       dict(variant=1, exact_color=1), dict(variant=1, verify=1), dict(variant=1, verify=1, exact_color=1)])
 def test_emulated_integrate_variants(ob, synth, kernel_kw):
     run_case(ob, synth, scene_kw=SMALL, vox=0.05, trunc=0.2, frames=2, **kernel_kw)
 
 
-def test_emulated_integrate_no_colour_and_negative_coordinates(ob, synth):
+@pytest.mark.parametrize("rev", REVS)
+def test_emulated_integrate_no_colour_and_negative_coordinates(ob, synth, rev):
     sc = dict(width=160, height=120, room=(4.0, 3.0, 2.5), room_min=(-2.0, -1.5, -1.25), n_frames=60)
-    run_case(ob, synth, scene_kw=sc, vox=0.04, trunc=0.2, frames=2, color=False)
+    run_case(ob, synth, scene_kw=sc, vox=0.04, trunc=0.2, frames=2, color=False, variant=rev)
 
 
-def test_emulated_integrate_hostile_depth(ob, synth):
+@pytest.mark.parametrize("rev", REVS)
+def test_emulated_integrate_hostile_depth(ob, synth, rev):
     """NaN, +-inf, negative, denormal and beyond-MaxDepth samples go through the same gates as in the reference"""
     def mutate(i, d):
         d = d.copy()
@@ -84,4 +95,6 @@ def test_emulated_integrate_hostile_depth(ob, synth):
         idx = rng.randint(0, d.size, 600)
         d.reshape(-1)[idx] = bad[rng.randint(0, len(bad), 600)]
         return d
-    run_case(ob, synth, scene_kw=SMALL, vox=0.05, trunc=0.2, frames=2, mutate=mutate)
+    run_case(ob, synth, scene_kw=SMALL, vox=0.05, trunc=0.2, frames=2, mutate=mutate, variant=rev)
+    if rev == 1:      # NaN / inf numerators leave the fast path: the out-of-line IEEE redo of a step is exercised
+        assert run_case.slow_steps > 0

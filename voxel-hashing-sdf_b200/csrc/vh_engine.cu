@@ -178,6 +178,8 @@ int vh_create(const vh_params* p, vh_engine** out) {
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
+  { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] == '1') ? 1 : 0; }
+  S.byte_bias = 0x4B000000u;
   // approximate-projection error bound (vh_integrate.cu, gate4): 6.9e-7 px per pixel of image extent
   S.round_eps = 7.5e-7f * (float)std::max(p->width, p->height) + 2e-5f;
 
@@ -223,7 +225,8 @@ int vh_create(const vh_params* p, vh_engine** out) {
   for (int i = 0; i < 2; i++) {
     ALLOC(e->d_depth[i], npx * sizeof(float));
     ALLOC(e->d_rgb[i], npx * 3);
-    ALLOC(e->d_px[i], npx * sizeof(uint2));
+    ALLOC(e->d_px[i], (npx + 1) * sizeof(uint2));    // + the sentinel record {depth 0, rgb 0} integrate_kernel_r1 reads for pixels outside the image
+    if (cudaMemset(e->d_px[i] + npx, 0, sizeof(uint2)) != cudaSuccess) { int rc = fail(VH_ERR_CUDA, "CUDA Error: cudaMemset of the frame sentinel"); free_engine(e); return rc; }
   }
 #undef ALLOC
   D.map.mask = e->capacity - 1;
