@@ -1,0 +1,92 @@
+"""GPU (B200): integrate_kernel_r1 (VH_INTEGRATE_REV=1) through the C ABI against the goldens and the oracle.
+
+The revision is opt-in and, when this file was written, had only been checked under CPU emulation
+(tests/test_emu_integrate.py) — the round's GPU budget was spent. The tests therefore run only with VH_TEST_REV1=1
+(tools/gpu_rev1.sh sets it); once they have passed on a B200 the revision can become the default and the gate can go.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import assert_triangles_match, assert_voxels_match, run_pair
+from util import CASES, engine_params, load_golden
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("VH_TEST_REV1") != "1", reason="opt-in kernel revision: set VH_TEST_REV1=1 (tools/gpu_rev1.sh)")]
+
+
+@pytest.fixture(params=["4", "3"], ids=["4ctas", "3ctas"])
+def rev1(request, monkeypatch):
+    monkeypatch.setenv("VH_INTEGRATE_REV", "1")
+    monkeypatch.setenv("VH_INTEGRATE_CTAS", request.param)
+
+
+@pytest.mark.parametrize("name", ["g8_color_holes", "g8_negative_coords"])
+def test_rev1_matches_reference_golden(name, vh, synth, rev1):
+    case, g = CASES[name], load_golden(name)
+    sc = synth.Scene(**case["scene"])
+    color = bool(case["scene"].get("color"))
+    with vh.TsdfEngine(engine_params(vh, sc, case)) as eng:
+        for i in range(case["frames"]):
+            eng.processFrame(*sc.frame(i))
+        assert_voxels_match(eng, g["keys"], g["sdf"], g["weight"], g["rgb"], color)
+        assert_triangles_match(*eng.triangles(), g["tri_xyz"], g["tri_rgb"], color)
+        cs = eng.checksum()
+        assert cs["sum_w"] == g["checksum"][1] and cs["n_observed"] == g["checksum"][2] and cs["n_negative"] == g["checksum"][3]
+
+
+def test_rev1_general_colour_path(vh, synth, rev1, monkeypatch):
+    monkeypatch.setenv("VH_INTEGRATE_EXACT_COLOR", "1")     # weights "above 65536": the general division sequence
+    name = "g8_color_holes"
+    case, g = CASES[name], load_golden(name)
+    sc = synth.Scene(**case["scene"])
+    with vh.TsdfEngine(engine_params(vh, sc, case)) as eng:
+        for i in range(case["frames"]):
+            eng.processFrame(*sc.frame(i))
+        assert_voxels_match(eng, g["keys"], g["sdf"], g["weight"], g["rgb"], True)
+
+
+def test_rev1_headline_sequence(vh, ob, synth, rev1):
+    """40 frames of BASELINE config 2 (the bench workload): per-frame counters, every voxel, the ordered mesh."""
+    sc = synth.make_scene("C2", color=True)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.005, trunc=0.025, max_depth=10.0)
+    run_pair(vh, ob, sc, case, frames=40, num_buckets=1 << 20, pool_blocks=1 << 19, tri_arena_bytes=2 << 30)
+
+
+def test_rev1_revisits_and_hostile_depth(vh, ob, synth, rev1):
+    """weights > 1 and NaN / inf / negative / denormal depth samples (the out-of-line IEEE redo of a step)"""
+    sc = synth.Scene(width=320, height=240, room=(5.0, 4.0, 2.6), n_frames=40, spheres=((3.9, 2.0, 1.0, 0.5),), color=True)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.02, trunc=0.1, max_depth=3.5)
+    o = ob.Oracle(__import__("util").oracle_params(ob, sc, case))
+    with vh.TsdfEngine(engine_params(vh, sc, case, num_buckets=1 << 18, pool_blocks=1 << 17)) as eng:
+        for i in range(12):
+            d, rgb, c2w = sc.frame(i)
+            rng = np.random.RandomState(11 + i)
+            bad = np.array([np.nan, np.inf, -np.inf, -1.0, 1e-40, 50.0, 0.0], np.float32)
+            idx = rng.randint(0, d.size, 2000)
+            d.reshape(-1)[idx] = bad[rng.randint(0, len(bad), 2000)]
+            o.process_frame(d, rgb, c2w)
+            eng.processFrame(d, rgb, c2w)
+            assert eng.stats().voxel_updates == o.last_updates, f"voxel updates differ in frame {i}"
+        keys = o.all_keys()
+        sdf, w, rgb_, _ = o.get_blocks(keys)
+        s2, w2, c2, found = eng.download_blocks(keys)
+        assert found.all()
+        assert np.array_equal(s2.view(np.uint32), sdf.view(np.uint32)) and np.array_equal(w2.view(np.uint32), w.view(np.uint32))
+        assert np.array_equal(c2, rgb_)
+
+
+def test_rev1_verify_mode_counts_no_disagreement(vh, synth, rev1, monkeypatch):
+    """VH_INTEGRATE_VERIFY=1: fast and IEEE formulations side by side inside the kernel, zero disagreements"""
+    monkeypatch.setenv("VH_INTEGRATE_VERIFY", "1")
+    sc = synth.make_scene("C2", color=True)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.005, trunc=0.025, max_depth=10.0)
+    with vh.TsdfEngine(engine_params(vh, sc, case, num_buckets=1 << 20, pool_blocks=1 << 19, tri_arena_bytes=1 << 30)) as eng:
+        total = 0
+        for i in range(6):
+            eng.processFrame(*sc.frame(i))
+            st = eng.stats()
+            total += st.voxel_updates
+            assert st.debug_mismatches == 0
+        assert total > 5e7
