@@ -84,3 +84,83 @@ class EmuMap:
         w = self.wgt.reshape(-1, 512)[slots]
         c = self.rgb4.reshape(-1, 512, 4)[slots]
         return s, w, c, slots
+
+
+# ---- the whole per-frame path under emulation (emu_engine.cpp) --------------------------------------------------------
+class EmuEngine:
+    """pack -> allocate -> integrate -> marching cubes with the engine's kernel sources on the CPU; mirrors the subset of
+    voxel-hashing-sdf_b200.TsdfEngine the parity tests use."""
+
+    def __init__(self, params, integrate_rev=0, cull=1, exact_color=0):
+        L = lib()
+        L.emu_create.restype = C.c_void_p
+        L.emu_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.emu_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_last_updates.restype = C.c_ulonglong
+        L.emu_last_triangles.restype = C.c_ulonglong
+        L.emu_block_triangles.restype = C.c_longlong
+        for f in ("emu_destroy", "emu_num_visible", "emu_last_updates", "emu_last_triangles", "emu_num_blocks"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.emu_visible_keys.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_all_keys.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_get_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.emu_block_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.L, self.params = L, params
+        self.h = L.emu_create(C.addressof(params), integrate_rev, cull, exact_color)
+        assert self.h, "emu_create rejected the parameters"
+
+    def close(self):
+        if self.h:
+            self.L.emu_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def process_frame(self, depth, rgb, c2w):
+        depth = np.ascontiguousarray(depth, np.float32)
+        c2w = np.ascontiguousarray(c2w, np.float32)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        rc = self.L.emu_process_frame(self.h, depth.ctypes.data, None if rgb is None else rgb.ctypes.data, c2w.ctypes.data)
+        assert rc == 0, f"map/engine error flags 0x{rc:x}"
+
+    num_visible = property(lambda s: s.L.emu_num_visible(s.h))
+    last_updates = property(lambda s: s.L.emu_last_updates(s.h))
+    last_triangles = property(lambda s: s.L.emu_last_triangles(s.h))
+    num_blocks = property(lambda s: s.L.emu_num_blocks(s.h))
+
+    def visible_keys(self):
+        out = np.zeros((max(self.num_visible, 1), 3), np.int32)
+        self.L.emu_visible_keys(self.h, out.ctypes.data)
+        return out[:self.num_visible]
+
+    def all_keys(self):
+        out = np.zeros((max(self.num_blocks, 1), 3), np.int32)
+        self.L.emu_all_keys(self.h, out.ctypes.data)
+        return out[:self.num_blocks]
+
+    def get_blocks(self, keys):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        n = len(keys)
+        sdf = np.zeros((n, 512), np.float32); w = np.zeros((n, 512), np.float32); rgb = np.zeros((n, 512, 3), np.uint8)
+        found = np.zeros(n, np.uint8); neg = np.zeros(n, np.int32)
+        self.L.emu_get_blocks(self.h, keys.ctypes.data, n, sdf.ctypes.data, w.ctypes.data, rgb.ctypes.data, found.ctypes.data, neg.ctypes.data)
+        return sdf, w, rgb, found.astype(bool), neg
+
+    def block_triangles(self, keys):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        n = self.L.emu_block_triangles(self.h, keys.ctypes.data, len(keys), None, None)
+        xyz = np.zeros((max(n, 1), 3, 3), np.float32); rgb = np.zeros((max(n, 1), 3, 3), np.uint8)
+        self.L.emu_block_triangles(self.h, keys.ctypes.data, len(keys), xyz.ctypes.data, rgb.ctypes.data)
+        return xyz[:n], rgb[:n]
+
+
+def mesh_order(keys, blocks_per_chunk=8):
+    """tsdf2mesh's block order (tsdf.cu:1786-1806): chunks x, y, z ascending, then the block inside the chunk"""
+    keys = np.asarray(keys, np.int64).reshape(-1, 3)
+    ch = np.floor_divide(keys, blocks_per_chunk)
+    order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0], ch[:, 2], ch[:, 1], ch[:, 0]))
+    return keys[order].astype(np.int32)

@@ -32,6 +32,7 @@
 #define __shared__ static
 #define __constant__ static
 #define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
 #define __CUDACC__ 1
 #define VH_HOST_EMU 1
 
@@ -82,6 +83,7 @@ struct Cta {
   dim3 bdim, gdim;
   void (*entry)(void*) = nullptr;
   void* arg = nullptr;
+  char* dyn_smem = nullptr;      // dynamic shared memory of the CTA (third launch parameter)
 };
 extern Cta* g_cta;
 extern unsigned long long g_collectives, g_events;
@@ -110,7 +112,7 @@ inline const unsigned long long* exchange(unsigned long long v) {
 
 void trampoline();
 // runs kernel(arg) for every thread of every CTA of the grid, CTAs one after the other
-void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg);
+void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg, size_t dyn_smem_bytes = 0);
 
 }  // namespace emu
 
@@ -218,6 +220,7 @@ static inline int __float2int_rz(float a) {   // saturating, NaN -> 0 like cvt.r
 }
 static inline int __float2int_rn(float a) { if (a != a) return 0; if (a >= 2147483648.0f) return 2147483647; if (a <= -2147483648.0f) return -2147483647 - 1; return (int)nearbyintf(a); }
 static inline int __float2int_rd(float a) { return __float2int_rz(floorf(a)); }
+static inline float __double2float_rn(double a) { return (float)a; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }

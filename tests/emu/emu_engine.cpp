@@ -1,0 +1,173 @@
+// tests/emu/emu_engine.cpp — the whole per-frame path (pack -> allocate -> integrate -> marching cubes) with the product's
+// own kernel sources executed on the CPU through tests/emu/cuda_runtime.h. TEST INFRASTRUCTURE ONLY (see emu_kernels.cpp):
+// part of tests/emu/libvh_emu.so, loaded by tests/test_emu_engine.py; libvhsdf.so never links or loads it.
+// The host side below restates the few lines of vh_create / reset_map / enqueue_stages that size and order the launches
+// (voxel-hashing-sdf_b200/csrc/vh_engine.cu); the parameter blocks come from the engine's own vh_params_host.h.
+#include <cuda_runtime.h>
+
+#include "../../voxel-hashing-sdf_b200/csrc/vh_alloc.cu"
+#include "../../voxel-hashing-sdf_b200/csrc/vh_mc.cu"
+#include "../../voxel-hashing-sdf_b200/csrc/vh_params_host.h"
+
+namespace vh {
+// defined in emu_kernels.cpp (which includes vh_integrate.cu)
+void emu_launch_pack(const float* depth, const uint8_t* rgb, uint2* out, int W, int H, float* tile_max, int* sched, FrameCounters* counters, uint32_t frame);
+void emu_launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* px, const DeviceView& D, bool color, int rev, int ctas);
+}
+
+using namespace vh;
+
+struct emu_engine {
+  vh_params P;
+  StaticParams S;
+  FrameParams F;
+  DeviceView D;
+  std::vector<u64> keys, key_heap;
+  std::vector<int> slots, free_list, neg_count, sched, visible, tri_count;
+  std::vector<uint32_t> stamps;
+  std::vector<float> sdf, wgt, tile_max;
+  std::vector<uchar4> rgb;
+  std::vector<McWork> mc_queue;
+  std::vector<vh_triangle> arena;
+  std::vector<unsigned long long> tri_offset;
+  std::vector<uint2> px;
+  std::vector<uint4> tables;
+  McQueueCtl mc_ctl[2];
+  int free_top = 0, heap_counter = 0, map_error = 0, engine_error = 0, mc_parity = 0;
+  uint32_t overflow_frame = 0;
+  unsigned long long arena_top = 0, updates_total = 0;
+  FrameCounters counters;
+  uint64_t frames = 0;
+  uint32_t integrate_launches = 0, weight_bound_bias = 0;
+  int rev = 0;
+};
+
+namespace {
+struct AllocArgs { StaticParams S; FrameParams F; const float* depth; DeviceView D; int tiles_x; };
+void run_alloc(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel(a->S, a->F, a->depth, a->D, a->tiles_x); }
+struct McArgs { StaticParams S; uint32_t frame; DeviceView D; const int* list; const int* list_count; int full_map; unsigned long long* out_offset; int* out_count;
+                McWork* queue; McQueueCtl* ctl; McQueueCtl* ctl_next; const uint4* tables; };
+void run_filter(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
+void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
+}  // namespace
+
+extern "C" {
+
+emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exact_color) {
+  if (!p || p->voxels_per_block != VPB || p->shard_count != 1) return nullptr;
+  emu_engine* e = new emu_engine;
+  e->P = *p;
+  StaticParams& S = e->S; memset(&S, 0, sizeof(S));
+  derive_static_params(*p, S);
+  S.verify = 0; S.integrate_ctas_per_sm = 4; S.integrate_cull = cull; S.integrate_two_steps = 0; S.integrate_rev = integrate_rev;
+  e->rev = integrate_rev; e->weight_bound_bias = exact_color ? 1u << 20 : 0u;
+  uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket, cap = 1024;      // vh_create
+  while (cap < want) cap <<= 1;
+  const size_t nb = (size_t)p->pool_blocks, rays = (size_t)S.nrx * S.nry;
+  DeviceView& D = e->D; memset(&D, 0, sizeof(D));
+  D.list_cap = (int)std::max(rays * (size_t)S.max_steps, nb);
+  e->keys.assign(cap, KEY_EMPTY); e->slots.assign(cap, -1); e->stamps.assign(cap, 0u);          // reset_map
+  e->free_list.resize(nb); for (size_t i = 0; i < nb; i++) e->free_list[i] = (int)(nb - 1 - i);   // init_free_list_kernel
+  e->free_top = (int)nb; e->key_heap.assign(nb, 0);
+  e->sdf.assign(nb * BLOCK_VOX, 0.0f); e->wgt.assign(nb * BLOCK_VOX, 0.0f);
+  if (S.use_color) e->rgb.assign(nb * BLOCK_VOX, uchar4{0, 0, 0, 0});
+  e->neg_count.assign(nb, 0); e->sched.assign(8 * 32, 0);
+  e->tile_max.assign((size_t)((p->width + 15) / 16) * ((p->height + 15) / 16), 0.0f);
+  e->visible.assign(D.list_cap, 0); e->mc_queue.resize(D.list_cap);
+  e->arena.resize(std::max<size_t>((size_t)p->tri_arena_bytes / sizeof(vh_triangle), 1024));
+  e->tri_offset.assign(nb, 0); e->tri_count.assign(nb, 0);
+  e->px.assign((size_t)p->width * p->height + 1, make_uint2(0u, 0u));                          // + the sentinel record
+  memset(e->mc_ctl, 0, sizeof(e->mc_ctl)); memset(&e->counters, 0, sizeof(e->counters));
+  {   // upload_mc_tables: expanded case tables as the mesh kernel copies them (tri 4096 B, then ntri 256 B)
+    static signed char tri[256][16]; static unsigned char ntri[256]; static unsigned short em[256];
+    vh_mc_expand_tables(tri, ntri, em);
+    e->tables.resize((sizeof(tri) + sizeof(ntri)) / sizeof(uint4));
+    memcpy(e->tables.data(), tri, sizeof(tri)); memcpy(reinterpret_cast<char*>(e->tables.data()) + sizeof(tri), ntri, sizeof(ntri));
+  }
+  D.map.keys = e->keys.data(); D.map.slots = e->slots.data(); D.map.mask = (uint32_t)cap - 1; D.map.free_list = e->free_list.data();
+  D.map.free_top = &e->free_top; D.map.key_heap = e->key_heap.data(); D.map.heap_counter = &e->heap_counter; D.map.error_flag = &e->map_error;
+  D.map.num_blocks = p->pool_blocks;
+  D.stamps = e->stamps.data(); D.sdf = e->sdf.data(); D.wgt = e->wgt.data(); D.rgb = S.use_color ? e->rgb.data() : nullptr;
+  D.sched = e->sched.data(); D.tile_max = e->tile_max.data(); D.neg_count = e->neg_count.data(); D.visible = e->visible.data();
+  D.counters = &e->counters; D.arena = e->arena.data(); D.arena_top = &e->arena_top; D.arena_cap = e->arena.size();
+  D.tri_offset = e->tri_offset.data(); D.tri_count = e->tri_count.data(); D.engine_error = &e->engine_error; D.overflow_frame = &e->overflow_frame;
+  D.updates_total = &e->updates_total; D.peers = nullptr; D.mc_queue = e->mc_queue.data(); D.mc_ctl = e->mc_ctl; D.mc_parity = &e->mc_parity;
+  return e;
+}
+
+void emu_destroy(emu_engine* e) { delete e; }
+
+// one frame, in the order of enqueue_stages for frames resident on the device: pack (resets the counters), allocate,
+// integrate, marching cubes over the visible list
+int emu_process_frame(emu_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+  const StaticParams& S = e->S; DeviceView& D = e->D;
+  derive_frame_params(e->P, e->S, c2w, e->F);
+  e->F.frame = (uint32_t)(++e->frames);
+  const uint8_t* rgb_in = S.use_color ? rgb : nullptr;
+  emu_launch_pack(depth, rgb_in, e->px.data(), S.W, S.H, D.tile_max, D.sched, D.counters, e->F.frame);
+  {
+    const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;     // launch_alloc_visible
+    const size_t smem = 2 * CHUNK_KEYS * sizeof(u64) + (size_t)S.max_steps * RAYS * sizeof(int);
+    AllocArgs a{S, e->F, depth, D, tiles_x};
+    emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_alloc, &a, smem);
+  }
+  e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
+  emu_launch_integrate(e->S, e->F, e->px.data(), D, rgb_in != nullptr, e->rev, 2);
+  if (e->P.mc_per_frame) {
+    McQueueCtl* ctl = D.mc_ctl + (e->mc_parity & 1);                                                // launch_marching_cubes
+    McQueueCtl* ctl_next = D.mc_ctl + ((e->mc_parity & 1) ^ 1);
+    e->mc_parity ^= 1;
+    McArgs m{S, e->F.frame, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, D.mc_queue, ctl, ctl_next, e->tables.data()};
+    emu::run_grid(dim3(3), dim3(256), run_filter, &m);
+    emu::run_grid(dim3(3), dim3(MC_THREADS), run_mesh, &m);
+  }
+  return e->map_error | (e->engine_error << 8);
+}
+
+int emu_num_visible(const emu_engine* e) { return e->counters.visible_count; }
+unsigned long long emu_last_updates(const emu_engine* e) { return e->counters.voxel_updates; }
+unsigned long long emu_last_triangles(const emu_engine* e) { return e->counters.triangles; }
+int emu_num_blocks(const emu_engine* e) { return e->heap_counter; }
+
+void emu_visible_keys(const emu_engine* e, int* out_xyz) {
+  for (int i = 0; i < e->counters.visible_count; i++) unpack_key(e->keys[e->visible[i]], out_xyz[3 * i], out_xyz[3 * i + 1], out_xyz[3 * i + 2]);
+}
+void emu_all_keys(const emu_engine* e, int* out_xyz) {
+  for (int i = 0; i < e->heap_counter; i++) unpack_key(e->key_heap[i], out_xyz[3 * i], out_xyz[3 * i + 1], out_xyz[3 * i + 2]);
+}
+static int find_slot(const emu_engine* e, int x, int y, int z) {
+  const u64 key = pack_key(x, y, z);
+  uint32_t h = hash_key(key) & e->D.map.mask;
+  for (;;) { const u64 cur = e->keys[h]; if (cur == key) return e->slots[h]; if (cur == KEY_EMPTY) return -1; h = (h + 1) & e->D.map.mask; }
+}
+// voxels of the given blocks: sdf, weight [n][512], rgb [n][512][3], found [n]; neg [n] = the kernel-maintained negative-voxel counter
+void emu_get_blocks(const emu_engine* e, const int* keys_xyz, int n, float* sdf, float* w, uint8_t* rgb, uint8_t* found, int* neg) {
+  for (int i = 0; i < n; i++) {
+    const int s = find_slot(e, keys_xyz[3 * i], keys_xyz[3 * i + 1], keys_xyz[3 * i + 2]);
+    found[i] = s >= 0;
+    if (s < 0) continue;
+    memcpy(sdf + (size_t)i * 512, &e->sdf[(size_t)s * 512], 512 * sizeof(float));
+    memcpy(w + (size_t)i * 512, &e->wgt[(size_t)s * 512], 512 * sizeof(float));
+    neg[i] = e->neg_count[s];
+    if (e->S.use_color) for (int v = 0; v < 512; v++) { const uchar4 c = e->rgb[(size_t)s * 512 + v]; uint8_t* o = rgb + ((size_t)i * 512 + v) * 3; o[0] = c.x; o[1] = c.y; o[2] = c.z; }
+  }
+}
+// stored triangles of the given blocks, concatenated in the given order: returns the count; xyz [T][3][3], rgb [T][3][3] (may be null to count)
+long long emu_block_triangles(const emu_engine* e, const int* keys_xyz, int n, float* xyz, uint8_t* rgb) {
+  long long t = 0;
+  for (int i = 0; i < n; i++) {
+    const int s = find_slot(e, keys_xyz[3 * i], keys_xyz[3 * i + 1], keys_xyz[3 * i + 2]);
+    if (s < 0) continue;
+    for (int k = 0; k < e->tri_count[s]; k++, t++) {
+      if (!xyz) continue;
+      const vh_triangle& T = e->arena[e->tri_offset[s] + k];
+      for (int v = 0; v < 3; v++) {
+        xyz[(t * 3 + v) * 3 + 0] = T.p[v].x; xyz[(t * 3 + v) * 3 + 1] = T.p[v].y; xyz[(t * 3 + v) * 3 + 2] = T.p[v].z;
+        rgb[(t * 3 + v) * 3 + 0] = T.p[v].r; rgb[(t * 3 + v) * 3 + 1] = T.p[v].g; rgb[(t * 3 + v) * 3 + 2] = T.p[v].b;
+      }
+    }
+  }
+  return t;
+}
+
+}  // extern "C"

@@ -30,6 +30,35 @@ void run_pack(void* p) {
 
 }  // namespace
 
+namespace vh {
+
+void emu_launch_pack(const float* depth, const uint8_t* rgb, uint2* out, int W, int H, float* tile_max, int* sched, FrameCounters* counters, uint32_t frame) {
+  PackArgs pa{depth, rgb, out, W, H, tile_max, sched, counters, frame};
+  emu::run_grid(dim3((W + 15) / 16, (H + 15) / 16), dim3(16, 16), run_pack, &pa);
+}
+
+// dispatch of launch_integrate (csrc/vh_integrate.cu) for the default tuning (one step at a time, 4 CTAs per SM), on `ctas` emulated CTAs
+void emu_launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* px, const DeviceView& D, bool color, int rev, int ctas) {
+  color = color && S.use_color;
+  IntegrateArgs ia{S, F, px, D, rev};
+  const bool cull = S.integrate_cull != 0;
+  void (*entry)(void*) = nullptr;
+  if (rev == 1) {
+    const bool delta = S.weight_bound <= 65536u;
+    entry = !color ? (cull ? run_r1<false, false, false, true> : run_r1<false, false, false, false>)
+          : delta ? (cull ? run_r1<true, false, true, true> : run_r1<true, false, true, false>)
+                  : (cull ? run_r1<true, false, false, true> : run_r1<true, false, false, false>);
+  } else {
+    const bool fast = S.weight_bound <= 4096u;
+    entry = !color ? (cull ? run_variant<false, false, false, false, true> : run_variant<false, false, false, false, false>)
+          : fast ? (cull ? run_variant<true, false, false, true, true> : run_variant<true, false, false, true, false>)
+                 : (cull ? run_variant<true, false, false, false, true> : run_variant<true, false, false, false, false>);
+  }
+  emu::run_grid(dim3(std::max(ctas, 1)), dim3(INT_THREADS), entry, &ia);
+}
+
+}  // namespace vh
+
 extern "C" {
 
 struct emu_integrate_io {

@@ -16,13 +16,15 @@ void trampoline() {
   swapcontext(&c->cur->ctx, &c->sched);
 }
 
-void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg) {
+void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg, size_t dyn_smem_bytes) {
   const int nthreads = (int)(block.x * block.y * block.z);
   const size_t stack_bytes = 256 << 10;
   Cta cta;
   cta.fibres.resize(nthreads);
   for (auto& f : cta.fibres) f.stack = (char*)malloc(stack_bytes);
   cta.bdim = block; cta.gdim = grid; cta.entry = entry; cta.arg = arg;
+  std::vector<char> dyn(dyn_smem_bytes + 16);
+  cta.dyn_smem = dyn.data() + (16 - (reinterpret_cast<uintptr_t>(dyn.data()) & 15)) % 16;
   Cta* const outer = g_cta;
   g_cta = &cta;
   for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {

@@ -127,7 +127,11 @@ __device__ __forceinline__ void ray_march(RayState& R, int steps, u64* __restric
 // serialise in L2: 24 % of the stall samples).
 __global__ void __launch_bounds__(ALLOC_THREADS)
 alloc_visible_kernel(const StaticParams S, const FrameParams F, const float* __restrict__ depth, const DeviceView D, int tiles_x) {
+#ifdef VH_HOST_EMU                                   // CPU emulation of the kernel sources (tests/emu, test infrastructure)
+  u64* dyn = reinterpret_cast<u64*>(emu::g_cta->dyn_smem);
+#else
   extern __shared__ u64 dyn[];                       // [2][CHUNK_KEYS] keys, then int first[max_steps * RAYS]
+#endif
   u64* skeys = dyn;
   int* s_first = reinterpret_cast<int*>(dyn + 2 * CHUNK_KEYS);
   __shared__ int s_cnt, s_base;
@@ -191,6 +195,7 @@ alloc_visible_kernel(const StaticParams S, const FrameParams F, const float* __r
     if (base + i < D.list_cap) D.visible[base + i] = s_first[i];
 }
 
+#ifndef VH_HOST_EMU
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st) {
   const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;
   const size_t smem = 2 * CHUNK_KEYS * sizeof(u64) + (size_t)S.max_steps * RAYS * sizeof(int);
@@ -198,6 +203,7 @@ void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const flo
     cudaFuncSetAttribute(alloc_visible_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   alloc_visible_kernel<<<tiles_x * tiles_y, ALLOC_THREADS, smem, st>>>(S, F, d_depth, D, tiles_x);
 }
+#endif  // !VH_HOST_EMU
 
 // ---- caller-supplied visible list (stage tests; vh_set_visible) ------------------------------------
 __global__ void set_visible_kernel(const DeviceView D, const u64* __restrict__ keys, int n, uint32_t frame) {
@@ -225,10 +231,12 @@ __global__ void set_visible_kernel(const DeviceView D, const u64* __restrict__ k
   }
 }
 
+#ifndef VH_HOST_EMU
 void launch_set_visible(const DeviceView& D, const u64* d_keys, int n, uint32_t frame, cudaStream_t st) {
   if (n <= 0) return;
   set_visible_kernel<<<(n + 255) / 256, 256, 0, st>>>(D, d_keys, n, frame);
 }
+#endif  // !VH_HOST_EMU
 
 // every allocated block, in key_heap order (full-map marching cubes, exports)
 __global__ void list_all_blocks_kernel(const DeviceView D, int* __restrict__ list, int* __restrict__ list_count) {
@@ -238,9 +246,11 @@ __global__ void list_all_blocks_kernel(const DeviceView D, int* __restrict__ lis
   if (i < n) list[i] = map_find(D.map, D.map.key_heap[i]);
 }
 
+#ifndef VH_HOST_EMU
 void launch_list_all_blocks(const DeviceView& D, int* list, int* list_count, cudaStream_t st) {
   const int n = D.map.num_blocks;
   list_all_blocks_kernel<<<(n + 255) / 256, 256, 0, st>>>(D, list, list_count);
 }
+#endif  // !VH_HOST_EMU
 
 }  // namespace vh

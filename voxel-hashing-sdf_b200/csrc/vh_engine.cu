@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "vh_engine_host.h"
+#include "vh_params_host.h"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -31,32 +32,10 @@ int fail(int code, const char* fmt, ...) {
 }
 extern "C" int vh_set_error_(int code, const char* msg) { g_err = msg ? msg : ""; return code; }
 
-// ---- frame constants on the host: getFrustumCenter / streamInCPU2GPU preamble (tsdf.cu:154-161, :197-206, :300-312)
-// compiled with -ffp-contract=off: plain float expressions in the reference's order
-static void host_pixel_to_world(const vh_params& P, const float* c2w, int px, int py, float z, float out[3]) {
-  const float x = ((float)px - P.cx) * z / P.fx;
-  const float y = ((float)py - P.cy) * z / P.fy;
-  out[0] = x * c2w[0] + y * c2w[1] + z * c2w[2] + c2w[3];
-  out[1] = x * c2w[4] + y * c2w[5] + z * c2w[6] + c2w[7];
-  out[2] = x * c2w[8] + y * c2w[9] + z * c2w[10] + c2w[11];
-}
-
+// ---- frame constants on the host: derive_frame_params (vh_params_host.h)
 void setup_frame(vh_engine* e, const float* c2w) {
-  FrameParams& F = e->F;
-  const vh_params& P = e->P;
-  memcpy(F.c2w, c2w, sizeof(F.c2w));
-  host_pixel_to_world(P, c2w, P.width / 2, P.height / 2, P.max_depth / 2, F.fc);
-  const float cs = e->S.chunk_size;
-  const int rng = (int)std::ceil((double)P.chunk_radius / (double)cs);
-  const int lo = P.max_chunk_num ? -P.max_chunk_num / 2 : INT32_MIN / 2;
-  const int hi = P.max_chunk_num ? P.max_chunk_num / 2 - 1 : INT32_MAX / 2;
-  for (int a = 0; a < 3; a++) {
-    const int cc = (int)floorf(F.fc[a] / cs);
-    F.cstart[a] = std::max(cc - rng, lo);
-    F.cend[a] = std::min(cc + rng, hi);
-  }
-  F.chunk_test_radius = (float)((double)0.5f * (double)P.chunk_radius * (double)sqrtf(3.0f) * 1.1);
-  F.frame = (uint32_t)(++e->frames);
+  derive_frame_params(e->P, e->S, c2w, e->F);
+  e->F.frame = (uint32_t)(++e->frames);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -160,28 +139,13 @@ int vh_create(const vh_params* p, vh_engine** out) {
   e->P = *p;
   e->num_sms = prop.multiProcessorCount;
   StaticParams& S = e->S;
-  S.W = p->width; S.H = p->height; S.fx = p->fx; S.fy = p->fy; S.cx = p->cx; S.cy = p->cy;
-  S.min_depth = p->min_depth; S.max_depth = p->max_depth; S.vox_size = p->vox_size; S.trunc = p->trunc_margin;
-  S.block_size = (float)VPB * p->vox_size;                                          // tsdf.cu:1326
-  S.chunk_size = (float)(p->blocks_per_chunk * VPB) * p->vox_size;                  // tsdf.cu:1271
-  S.half_vox = 0.5f * p->vox_size;
-  S.stride = p->dda_stride; S.max_steps = p->max_ray_steps; S.bpc = p->blocks_per_chunk;
-  const int T = 8;                                                                  // T_PER_BLOCK launch shape, tsdf.cu:2263-2264
-  const int gx = (p->width / p->dda_stride + T - 1) / T * T, gy = (p->height / p->dda_stride + T - 1) / T * T;
-  S.nrx = std::min(gx, (p->width + p->dda_stride - 1) / p->dda_stride);
-  S.nry = std::min(gy, (p->height + p->dda_stride - 1) / p->dda_stride);
-  S.use_color = p->use_color ? 1 : 0;
-  S.shard_rank = (uint32_t)p->shard_rank; S.shard_count = (uint32_t)p->shard_count;
-  S.shard_group = p->shard_group > 0 ? p->shard_group : p->blocks_per_chunk;
+  derive_static_params(*p, S);
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '2' && v[0] <= '4') ? v[0] - '0' : 4; }   // tuning knobs
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] == '1') ? 1 : 0; }
-  S.byte_bias = 0x4B000000u;
-  // approximate-projection error bound (vh_integrate.cu, gate4): 6.9e-7 px per pixel of image extent
-  S.round_eps = 7.5e-7f * (float)std::max(p->width, p->height) + 2e-5f;
 
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket;
   uint64_t cap = 1024;

@@ -35,6 +35,7 @@ __constant__ unsigned short c_edge_mask[256];
 
 static uint4* g_tables_dev[16] = {};          // per device: expanded case tables in global memory (mesh kernel copies them to shared)
 
+#ifndef VH_HOST_EMU      // (the CPU emulation of the kernels, tests/emu, expands the tables itself)
 void upload_mc_tables() {
   for (int k = 0; k < 8; k++)
     if (corner_ox(k) != VH_MC_CORNER_OFFSET[k][0] || corner_oy(k) != VH_MC_CORNER_OFFSET[k][1] || corner_oz(k) != VH_MC_CORNER_OFFSET[k][2]) abort();
@@ -55,6 +56,8 @@ void upload_mc_tables() {
     cudaMemcpy(reinterpret_cast<char*>(g_tables_dev[dev & 15]) + sizeof(tri), ntri, sizeof(ntri), cudaMemcpyHostToDevice);
   }
 }
+
+#endif  // !VH_HOST_EMU
 
 struct Vtx { float x, y, z; uint32_t c; };   // c = r | g<<8 | b<<16
 
@@ -370,6 +373,7 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
 
+#ifndef VH_HOST_EMU
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count, int full_map,
                            unsigned long long* out_offset, int* out_count, int num_sms, cudaStream_t st) {
   int dev = 0;
@@ -387,5 +391,6 @@ void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const De
     mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
   }
 }
+#endif  // !VH_HOST_EMU
 
 }  // namespace vh
