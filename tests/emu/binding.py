@@ -96,6 +96,9 @@ class EmuEngine:
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.emu_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_phase_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_phase_mc.argtypes = [C.c_void_p]
+        L.emu_connect.argtypes = [C.c_void_p, C.c_int]
         L.emu_last_updates.restype = C.c_ulonglong
         L.emu_last_triangles.restype = C.c_ulonglong
         L.emu_block_triangles.restype = C.c_longlong
@@ -125,6 +128,17 @@ class EmuEngine:
         c2w = np.ascontiguousarray(c2w, np.float32)
         rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
         rc = self.L.emu_process_frame(self.h, depth.ctypes.data, None if rgb is None else rgb.ctypes.data, c2w.ctypes.data)
+        assert rc == 0, f"map/engine error flags 0x{rc:x}"
+
+    def phase_integrate(self, depth, rgb, c2w):
+        depth = np.ascontiguousarray(depth, np.float32)
+        c2w = np.ascontiguousarray(c2w, np.float32)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        rc = self.L.emu_phase_integrate(self.h, depth.ctypes.data, None if rgb is None else rgb.ctypes.data, c2w.ctypes.data)
+        assert rc == 0, f"map/engine error flags 0x{rc:x}"
+
+    def phase_mc(self):
+        rc = self.L.emu_phase_mc(self.h)
         assert rc == 0, f"map/engine error flags 0x{rc:x}"
 
     num_visible = property(lambda s: s.L.emu_num_visible(s.h))
@@ -164,3 +178,30 @@ def mesh_order(keys, blocks_per_chunk=8):
     ch = np.floor_divide(keys, blocks_per_chunk)
     order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0], ch[:, 2], ch[:, 1], ch[:, 0]))
     return keys[order].astype(np.int32)
+
+
+class EmuGroup:
+    """N emulated ranks of one sharded map (vh_shard_connect / vh_integrate_sharded): phase 1 on every rank, barrier,
+    phase 2 on every rank with the peers' tables and planes in reach."""
+
+    def __init__(self, make_params, n, **kw):
+        self.ranks = [EmuEngine(make_params(r, n), **kw) for r in range(n)]
+        arr = (C.c_void_p * n)(*[e.h for e in self.ranks])
+        rc = self.ranks[0].L.emu_connect(arr, n)
+        assert rc == 0, f"emu_connect failed: {rc}"
+
+    def close(self):
+        for e in self.ranks:
+            e.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def process_frame(self, depth, rgb, c2w):
+        for e in self.ranks:
+            e.phase_integrate(depth, rgb, c2w)
+        for e in self.ranks:
+            e.phase_mc()

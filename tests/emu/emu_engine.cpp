@@ -40,6 +40,7 @@ struct emu_engine {
   uint64_t frames = 0;
   uint32_t integrate_launches = 0, weight_bound_bias = 0;
   int rev = 0;
+  PeerTable peers;               // multi-GPU emulation: every shard's tables and planes (plain host pointers here)
 };
 
 namespace {
@@ -47,6 +48,8 @@ struct AllocArgs { StaticParams S; FrameParams F; const float* depth; DeviceView
 void run_alloc(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel(a->S, a->F, a->depth, a->D, a->tiles_x); }
 struct McArgs { StaticParams S; uint32_t frame; DeviceView D; const int* list; const int* list_count; int full_map; unsigned long long* out_offset; int* out_count;
                 McWork* queue; McQueueCtl* ctl; McQueueCtl* ctl_next; const uint4* tables; };
+void run_filter_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
+void run_mesh_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 void run_filter(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 }  // namespace
@@ -54,7 +57,7 @@ void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<fal
 extern "C" {
 
 emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exact_color) {
-  if (!p || p->voxels_per_block != VPB || p->shard_count != 1) return nullptr;
+  if (!p || p->voxels_per_block != VPB || p->shard_count < 1 || p->shard_count > MAX_SHARDS) return nullptr;
   emu_engine* e = new emu_engine;
   e->P = *p;
   StaticParams& S = e->S; memset(&S, 0, sizeof(S));
@@ -97,9 +100,10 @@ emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exac
 
 void emu_destroy(emu_engine* e) { delete e; }
 
-// one frame, in the order of enqueue_stages for frames resident on the device: pack (resets the counters), allocate,
-// integrate, marching cubes over the visible list
-int emu_process_frame(emu_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+// One frame in two phases. Single map: the order of enqueue_stages for frames resident on the device — pack (resets the
+// counters), allocate, integrate; then marching cubes over the visible list. Sharded map (vh_integrate_sharded): every
+// rank runs phase 1 on the broadcast frame, a barrier, every rank runs phase 2 reading its peers' tables and planes.
+int emu_phase_integrate(emu_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
   const StaticParams& S = e->S; DeviceView& D = e->D;
   derive_frame_params(e->P, e->S, c2w, e->F);
   e->F.frame = (uint32_t)(++e->frames);
@@ -113,15 +117,42 @@ int emu_process_frame(emu_engine* e, const float* depth, const uint8_t* rgb, con
   }
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   emu_launch_integrate(e->S, e->F, e->px.data(), D, rgb_in != nullptr, e->rev, 2);
+  return e->map_error | (e->engine_error << 8);
+}
+
+int emu_phase_mc(emu_engine* e) {
+  const StaticParams& S = e->S; DeviceView& D = e->D;
   if (e->P.mc_per_frame) {
     McQueueCtl* ctl = D.mc_ctl + (e->mc_parity & 1);                                                // launch_marching_cubes
     McQueueCtl* ctl_next = D.mc_ctl + ((e->mc_parity & 1) ^ 1);
     e->mc_parity ^= 1;
     McArgs m{S, e->F.frame, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, D.mc_queue, ctl, ctl_next, e->tables.data()};
-    emu::run_grid(dim3(3), dim3(256), run_filter, &m);
-    emu::run_grid(dim3(3), dim3(MC_THREADS), run_mesh, &m);
+    const bool sharded = S.shard_count > 1 && D.peers;
+    emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
+    emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
   }
   return e->map_error | (e->engine_error << 8);
+}
+
+int emu_process_frame(emu_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+  const int rc = emu_phase_integrate(e, depth, rgb, c2w);
+  return rc | emu_phase_mc(e);
+}
+
+// vh_shard_connect: every rank gets a view of every rank's table and planes (CUDA-IPC mappings on the GPU, pointers here)
+int emu_connect(emu_engine** ranks, int n) {
+  if (n < 1 || n > MAX_SHARDS) return -1;
+  for (int r = 0; r < n; r++) if (!ranks[r] || (int)ranks[r]->S.shard_count != n || (int)ranks[r]->S.shard_rank != r) return -2;
+  for (int r = 0; r < n; r++) {
+    PeerTable& T = ranks[r]->peers; memset(&T, 0, sizeof(T));
+    for (int q = 0; q < n; q++) {
+      const DeviceView& Q = ranks[q]->D;
+      T.v[q].keys = Q.map.keys; T.v[q].slots = Q.map.slots; T.v[q].stamps = Q.stamps; T.v[q].neg_count = Q.neg_count; T.v[q].sdf = Q.sdf; T.v[q].rgb = Q.rgb;
+      T.v[q].mask = Q.map.mask;
+    }
+    ranks[r]->D.peers = &ranks[r]->peers;
+  }
+  return 0;
 }
 
 int emu_num_visible(const emu_engine* e) { return e->counters.visible_count; }

@@ -81,3 +81,45 @@ def test_emulated_engine_matches_reference_golden(name, vh, synth):
         assert found.all() and np.array_equal(s, g["sdf"]) and np.array_equal(w, g["weight"]) and np.array_equal(c, g["rgb"])
         xyz, trgb = e.block_triangles(mesh_order(g["keys"]))
         assert np.array_equal(xyz, g["tri_xyz"]) and np.array_equal(trgb, g["tri_rgb"])
+
+
+@pytest.mark.parametrize("nranks,group", [(2, 8), (3, 1)])
+def test_emulated_sharded_map_equals_single_map(vh, ob, synth, nranks, group):
+    """one map sharded by block-coordinate hash over N emulated ranks (ownership filter in the allocation kernel, remote
+    table probes and halo reads in both marching-cubes kernels): the union is the oracle's single map, bit for bit"""
+    from emu.binding import EmuGroup
+    sc = synth.Scene(**SMALL)
+    o = ob.Oracle(oracle_params(ob, sc, CASE))
+
+    def make(rank, n):
+        return engine_params(vh, sc, CASE, num_buckets=1 << 12, pool_blocks=1 << 12, tri_arena_bytes=8 << 20, shard_rank=rank, shard_count=n,
+                             shard_group=group)
+
+    with EmuGroup(make, nranks) as g:
+        for i in range(3):
+            d, rgb, c2w = sc.frame(i)
+            o.process_frame(d, rgb, c2w)
+            g.process_frame(d, rgb, c2w)
+            vis = [key_set(e.visible_keys()) for e in g.ranks]
+            assert sum(len(v) for v in vis) == o.num_visible and set().union(*vis) == key_set(o.visible_keys()), f"frame {i}: visible sets"
+            assert sum(e.last_updates for e in g.ranks) == o.last_updates
+            assert sum(e.last_triangles for e in g.ranks) == o.last_triangles, f"frame {i}: triangle counts"
+        assert all(e.num_blocks > 0 for e in g.ranks), "a rank owns nothing: the case does not exercise sharding"
+        keys = o.all_keys()
+        owner = np.array([vh.owner_of_block(int(k[0]), int(k[1]), int(k[2]), nranks, group) for k in keys])
+        so, wo, co, _ = o.get_blocks(keys)
+        for r, e in enumerate(g.ranks):
+            mine = keys[owner == r]
+            assert key_set(e.all_keys()) == key_set(mine), f"rank {r} holds blocks it does not own (or misses some)"
+            s, w, c, found, neg = e.get_blocks(mine)
+            assert found.all()
+            assert np.array_equal(s.view(np.uint32), so[owner == r].view(np.uint32)) and np.array_equal(w, wo[owner == r]) and np.array_equal(c, co[owner == r])
+        # gathered mesh: blocks in tsdf2mesh order, each fetched from its owner
+        xyz_o, rgb_o = o.triangles()
+        parts = []
+        for k in mesh_order(keys):
+            r = vh.owner_of_block(int(k[0]), int(k[1]), int(k[2]), nranks, group)
+            parts.append(g.ranks[r].block_triangles(k[None, :]))
+        xyz = np.concatenate([p[0] for p in parts]) if parts else np.zeros((0, 3, 3), np.float32)
+        trgb = np.concatenate([p[1] for p in parts]) if parts else np.zeros((0, 3, 3), np.uint8)
+        assert xyz.shape == xyz_o.shape and np.array_equal(xyz.view(np.uint32), xyz_o.view(np.uint32)) and np.array_equal(trgb, rgb_o)
