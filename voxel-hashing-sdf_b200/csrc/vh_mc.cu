@@ -381,8 +381,12 @@ void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const De
   McQueueCtl* ctl = D.mc_ctl + (*D.mc_parity & 1);
   McQueueCtl* ctl_next = D.mc_ctl + ((*D.mc_parity & 1) ^ 1);
   *D.mc_parity ^= 1;
-  const int fgrid = num_sms * 4;
-  const int mgrid = num_sms * 5;                 // 5 CTAs of 4 warps fit an SM (36.7 KB of shared memory each)
+  // launch shapes; the environment overrides exist for sweeps on the GPU box (both kernels are latency-bound: the filter
+  // walks chains of dependent look-ups at 26 registers per thread, so 8 CTAs per SM fit)
+  static const int filter_ctas = [] { const char* v = getenv("VH_MC_FILTER_CTAS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 8 ? n : 4; }();
+  static const int mesh_ctas = [] { const char* v = getenv("VH_MC_MESH_CTAS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 6 ? n : 5; }();
+  const int fgrid = num_sms * filter_ctas;
+  const int mgrid = num_sms * mesh_ctas;         // 5 CTAs of 4 warps fit an SM (36.7 KB of shared memory each)
   if (S.shard_count > 1 && D.peers) {
     mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
     mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
