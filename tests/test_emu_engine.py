@@ -123,3 +123,44 @@ def test_emulated_sharded_map_equals_single_map(vh, ob, synth, nranks, group):
         xyz = np.concatenate([p[0] for p in parts]) if parts else np.zeros((0, 3, 3), np.float32)
         trgb = np.concatenate([p[1] for p in parts]) if parts else np.zeros((0, 3, 3), np.uint8)
         assert xyz.shape == xyz_o.shape and np.array_equal(xyz.view(np.uint32), xyz_o.view(np.uint32)) and np.array_equal(trgb, rgb_o)
+
+
+def test_emulated_engine_other_launch_shapes(vh, ob, synth):
+    """non-default run-time values of the reference's macros: DDA stride 7, 160 ray steps (a larger dynamic shared-memory
+    carve-out in the allocation kernel), unbounded chunk world, 16:9 image"""
+    sc = dict(width=192, height=108, room=(5.0, 4.0, 2.6), room_min=(-2.5, -2.0, -1.3), n_frames=60, color=True)
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.03, trunc=0.09, max_depth=5.0)
+    over = dict(max_chunk_num=0, max_ray_steps=160, dda_stride=7)
+    s = synth.Scene(**sc)
+    o = ob.Oracle(oracle_params(ob, s, case, **over))
+    with EmuEngine(engine_params(vh, s, case, num_buckets=1 << 12, pool_blocks=1 << 13, tri_arena_bytes=16 << 20, **over)) as e:
+        for i in range(2):
+            d, rgb, c2w = s.frame(i)
+            o.process_frame(d, rgb, c2w)
+            e.process_frame(d, rgb, c2w)
+            assert key_set(e.visible_keys()) == key_set(o.visible_keys())
+            assert e.last_updates == o.last_updates and e.last_triangles == o.last_triangles
+        keys = o.all_keys()
+        so, wo, co, _ = o.get_blocks(keys)
+        se, we, ce, found, _ = e.get_blocks(keys)
+        assert found.all() and np.array_equal(se, so) and np.array_equal(we, wo) and np.array_equal(ce, co)
+        xyz_o, _ = o.triangles()
+        xyz_e, _ = e.block_triangles(mesh_order(keys))
+        assert np.array_equal(xyz_e, xyz_o)
+
+
+def test_emulated_engine_pool_and_table_exhaustion_raise_flags(vh, synth):
+    """the reference throws "out of block memory" (blockalloc.h:51) / asserts on a full table (vhashing.h:104-112); the
+    kernels raise sticky error bits instead (the C ABI turns them into VH_ERR_*), keep running and never write out of bounds"""
+    sc = synth.Scene(**SMALL)
+    d, rgb, c2w = sc.frame(0)
+    with EmuEngine(engine_params(vh, sc, CASE, num_buckets=1 << 12, pool_blocks=40, tri_arena_bytes=8 << 20)) as e:      # ~200 blocks wanted
+        rc = e.process_frame(d, rgb, c2w, check=False)
+        assert rc & 2, "MAP_POOL_FULL not raised"
+        assert e.num_blocks >= 40
+    with EmuEngine(engine_params(vh, sc, CASE, num_buckets=16, entries_per_bucket=4, pool_blocks=1 << 12, tri_arena_bytes=8 << 20)) as e:   # capacity clamps to 1024
+        rc = 0
+        for i in range(0, 40, 4):
+            d, rgb, c2w = sc.frame(i)
+            rc |= e.process_frame(d, rgb, c2w, check=False)
+        assert rc & 1, "MAP_TABLE_FULL not raised"
