@@ -39,31 +39,71 @@ struct emu_engine {
   FrameCounters counters;
   uint64_t frames = 0;
   uint32_t integrate_launches = 0, weight_bound_bias = 0;
-  int rev = 0;
+  int rev = 0, alloc_rev = 0;
   PeerTable peers;               // multi-GPU emulation: every shard's tables and planes (plain host pointers here)
 };
 
 namespace {
 struct AllocArgs { StaticParams S; FrameParams F; const float* depth; DeviceView D; int tiles_x; };
 void run_alloc(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel(a->S, a->F, a->depth, a->D, a->tiles_x); }
+void run_alloc_r1(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel_r1(a->S, a->F, a->depth, a->D, a->tiles_x); }
 struct McArgs { StaticParams S; uint32_t frame; DeviceView D; const int* list; const int* list_count; int full_map; unsigned long long* out_offset; int* out_count;
                 McWork* queue; McQueueCtl* ctl; McQueueCtl* ctl_next; const uint4* tables; };
 void run_filter_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_mesh_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 void run_filter(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
+// test-only kernel: the step-by-step DDA (ray_march) and the merge formulation (merge_fill_keys) of the same tile of rays,
+// compared key by key; out[0] += mismatching steps, out[1] += steps compared, out[2] += non-empty keys
+struct MarchCmpArgs { StaticParams S; FrameParams F; const float* depth; int tiles_x; unsigned long long* out; };
+void run_march_compare(void* p) {
+  MarchCmpArgs* a = static_cast<MarchCmpArgs*>(p);
+  const StaticParams& S = a->S;
+  const int K = S.max_steps, tid = threadIdx.x;
+  u64* skeys = reinterpret_cast<u64*>(emu::g_cta->dyn_smem);
+  float* sT = reinterpret_cast<float*>(skeys + (size_t)K * RAYS);
+  u64* seq = reinterpret_cast<u64*>(sT + (size_t)RAYS * 3 * K);      // [K][RAYS] keys of the sequential march
+  static int s_death[RAYS];
+  const int tile_x = blockIdx.x % a->tiles_x, tile_y = blockIdx.x / a->tiles_x;
+  merge_fill_keys(S, a->F, a->depth, tile_x, tile_y, skeys, sT, s_death);
+  if (tid < RAYS) {
+    RayState R;
+    ray_setup(S, a->F, a->depth, tile_x * RAYS_X + (tid & (RAYS_X - 1)), tile_y * RAYS_Y + (tid / RAYS_X), R);
+    ray_march(R, K, seq + tid);
+    for (int s = 0; s < K; s++) {
+      const u64 m = s <= s_death[tid] ? skeys[s * RAYS + tid] : KEY_EMPTY;
+      a->out[0] += m != seq[s * RAYS + tid];
+      a->out[1] += 1;
+      a->out[2] += seq[s * RAYS + tid] != KEY_EMPTY;
+    }
+  }
+}
 }  // namespace
 
 extern "C" {
 
-emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exact_color) {
+// the two DDA formulations over every ray of one frame: out3 = {mismatching steps, steps compared, non-empty keys}
+void emu_compare_march(const vh_params* p, const float* depth, const float* c2w, unsigned long long* out3) {
+  StaticParams S; memset(&S, 0, sizeof(S));
+  derive_static_params(*p, S);
+  FrameParams F; memset(&F, 0, sizeof(F));
+  derive_frame_params(*p, S, c2w, F);
+  F.frame = 1;
+  out3[0] = out3[1] = out3[2] = 0;
+  const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;
+  MarchCmpArgs a{S, F, depth, tiles_x, out3};
+  const size_t smem = (size_t)S.max_steps * RAYS * sizeof(u64) * 2 + (size_t)RAYS * 3 * S.max_steps * sizeof(float);
+  emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_march_compare, &a, smem);
+}
+
+emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exact_color, int alloc_rev) {
   if (!p || p->voxels_per_block != VPB || p->shard_count < 1 || p->shard_count > MAX_SHARDS) return nullptr;
   emu_engine* e = new emu_engine;
   e->P = *p;
   StaticParams& S = e->S; memset(&S, 0, sizeof(S));
   derive_static_params(*p, S);
   S.verify = 0; S.integrate_ctas_per_sm = 4; S.integrate_cull = cull; S.integrate_two_steps = 0; S.integrate_rev = integrate_rev;
-  e->rev = integrate_rev; e->weight_bound_bias = exact_color ? 1u << 20 : 0u;
+  e->rev = integrate_rev; e->alloc_rev = alloc_rev; e->weight_bound_bias = exact_color ? 1u << 20 : 0u;
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket, cap = 1024;      // vh_create
   while (cap < want) cap <<= 1;
   const size_t nb = (size_t)p->pool_blocks, rays = (size_t)S.nrx * S.nry;
@@ -113,7 +153,8 @@ int emu_phase_integrate(emu_engine* e, const float* depth, const uint8_t* rgb, c
     const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;     // launch_alloc_visible
     const size_t smem = 2 * CHUNK_KEYS * sizeof(u64) + (size_t)S.max_steps * RAYS * sizeof(int);
     AllocArgs a{S, e->F, depth, D, tiles_x};
-    emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_alloc, &a, smem);
+    if (e->alloc_rev == 1) emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_alloc_r1, &a, alloc_r1_smem_bytes(S.max_steps));
+    else emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_alloc, &a, smem);
   }
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   emu_launch_integrate(e->S, e->F, e->px.data(), D, rgb_in != nullptr, e->rev, 2);

@@ -12,11 +12,11 @@ from emu.binding import EmuEngine, mesh_order
 from util import CASES, engine_params, key_set, load_golden, oracle_params
 
 
-def run_pair(vh, ob, synth, scene_kw, case, frames, rev=0, mutate=None, **eng_over):
+def run_pair(vh, ob, synth, scene_kw, case, frames, rev=0, alloc_rev=0, mutate=None, **eng_over):
     sc = synth.Scene(**scene_kw)
     color = bool(case["scene"].get("color"))
     o = ob.Oracle(oracle_params(ob, sc, case))
-    with EmuEngine(engine_params(vh, sc, case, **eng_over), integrate_rev=rev) as e:
+    with EmuEngine(engine_params(vh, sc, case, **eng_over), integrate_rev=rev, alloc_rev=alloc_rev) as e:
         for i in range(frames):
             d, rgb, c2w = sc.frame(i)
             if mutate is not None:
@@ -50,16 +50,19 @@ SMALL = dict(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=60, spheres=(
 CASE = dict(scene=dict(color=True), vpb=8, vox_size=0.04, trunc=0.2, max_depth=3.0)
 
 
-@pytest.mark.parametrize("rev", [0, 1])
-def test_emulated_engine_matches_oracle(vh, ob, synth, rev):
-    nblocks, ntris = run_pair(vh, ob, synth, SMALL, CASE, frames=3, rev=rev, num_buckets=1 << 12, pool_blocks=1 << 12, tri_arena_bytes=8 << 20)
+# kernel revisions (integrate, allocation): 0 = shipped defaults, 1 = opt-in (VH_INTEGRATE_REV=1 / VH_ALLOC_REV=1)
+@pytest.mark.parametrize("rev,alloc_rev", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_emulated_engine_matches_oracle(vh, ob, synth, rev, alloc_rev):
+    nblocks, ntris = run_pair(vh, ob, synth, SMALL, CASE, frames=3, rev=rev, alloc_rev=alloc_rev, num_buckets=1 << 12, pool_blocks=1 << 12,
+                              tri_arena_bytes=8 << 20)
     assert nblocks > 200 and ntris > 1000
 
 
-def test_emulated_engine_negative_coordinates_no_colour(vh, ob, synth):
+@pytest.mark.parametrize("alloc_rev", [0, 1])
+def test_emulated_engine_negative_coordinates_no_colour(vh, ob, synth, alloc_rev):
     sc = dict(width=160, height=120, room=(4.0, 3.0, 2.5), room_min=(-2.0, -1.5, -1.25), n_frames=60, holes=0.02)
     case = dict(scene={}, vpb=8, vox_size=0.04, trunc=0.2, max_depth=3.0)
-    run_pair(vh, ob, synth, sc, case, frames=3, num_buckets=1 << 12, pool_blocks=1 << 12, tri_arena_bytes=8 << 20)
+    run_pair(vh, ob, synth, sc, case, frames=3, alloc_rev=alloc_rev, num_buckets=1 << 12, pool_blocks=1 << 12, tri_arena_bytes=8 << 20)
 
 
 def test_emulated_engine_tiny_table_probes_and_wraps(vh, ob, synth):
@@ -125,7 +128,8 @@ def test_emulated_sharded_map_equals_single_map(vh, ob, synth, nranks, group):
         assert xyz.shape == xyz_o.shape and np.array_equal(xyz.view(np.uint32), xyz_o.view(np.uint32)) and np.array_equal(trgb, rgb_o)
 
 
-def test_emulated_engine_other_launch_shapes(vh, ob, synth):
+@pytest.mark.parametrize("alloc_rev", [0, 1])
+def test_emulated_engine_other_launch_shapes(vh, ob, synth, alloc_rev):
     """non-default run-time values of the reference's macros: DDA stride 7, 160 ray steps (a larger dynamic shared-memory
     carve-out in the allocation kernel), unbounded chunk world, 16:9 image"""
     sc = dict(width=192, height=108, room=(5.0, 4.0, 2.6), room_min=(-2.5, -2.0, -1.3), n_frames=60, color=True)
@@ -133,7 +137,7 @@ def test_emulated_engine_other_launch_shapes(vh, ob, synth):
     over = dict(max_chunk_num=0, max_ray_steps=160, dda_stride=7)
     s = synth.Scene(**sc)
     o = ob.Oracle(oracle_params(ob, s, case, **over))
-    with EmuEngine(engine_params(vh, s, case, num_buckets=1 << 12, pool_blocks=1 << 13, tri_arena_bytes=16 << 20, **over)) as e:
+    with EmuEngine(engine_params(vh, s, case, num_buckets=1 << 12, pool_blocks=1 << 13, tri_arena_bytes=16 << 20, **over), alloc_rev=alloc_rev) as e:
         for i in range(2):
             d, rgb, c2w = s.frame(i)
             o.process_frame(d, rgb, c2w)
@@ -164,3 +168,49 @@ def test_emulated_engine_pool_and_table_exhaustion_raise_flags(vh, synth):
             d, rgb, c2w = sc.frame(i)
             rc |= e.process_frame(d, rgb, c2w, check=False)
         assert rc & 1, "MAP_TABLE_FULL not raised"
+
+
+@pytest.mark.parametrize("alloc_rev", [0, 1])
+def test_emulated_allocation_dda_ties(vh, ob, synth, alloc_rev):
+    """axis-aligned poses with the camera on block boundaries: for the pixels on the image diagonals two axes of the DDA
+    cross block faces at exactly the same ray parameter, so the reference's tie rule decides which block is visited
+    (tsdf.cu:2217-2233: x only if strictly smallest, then z only if strictly before y). The step-by-step kernel and the
+    merge formulation of revision 1 must both reproduce the oracle's visible sets."""
+    sc = synth.Scene(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=4, radius_frac=0.0, color=False)
+    case = dict(scene={}, vpb=8, vox_size=0.03125, trunc=0.1, max_depth=3.0)      # 0.25 m blocks: the camera (2, 1.5, 1.25) sits on block faces
+    o = ob.Oracle(oracle_params(ob, sc, case))
+    ties = 0
+    with EmuEngine(engine_params(vh, sc, case, num_buckets=1 << 13, pool_blocks=1 << 13, tri_arena_bytes=16 << 20, mc_per_frame=0), alloc_rev=alloc_rev) as e:
+        for i in range(4):
+            d, rgb, c2w = sc.frame(i)
+            o.begin_frame(c2w); o.stage_allocate(d)
+            e.process_frame(d, None, c2w)
+            assert key_set(e.visible_keys()) == key_set(o.visible_keys()), f"visible set differs in frame {i}"
+            o.stage_integrate(d, None)
+            # count rays with an exact tie between two axes' first crossing times, to be sure the case bites
+            m = c2w.reshape(4, 4)
+            for v in range(0, 120, 10):
+                for u in range(0, 160, 10):
+                    dirc = m[:3, :3] @ np.array([(u - sc.cx) / sc.fx, (v - sc.cy) / sc.fy, 1.0])
+                    a = np.abs(dirc)
+                    ties += int(np.sum(np.isclose(a[:, None], a[None, :], rtol=0, atol=1e-9)) > 3)
+    assert ties > 20
+
+
+def test_emulated_dda_merge_equals_step_by_step_march(vh, synth):
+    """allocation revision 1 replaces the sequential 3-D DDA by a three-way merge of per-axis crossing times; here the two
+    are compared key by key, step by step, for every sampled ray — generic poses and the axis-aligned tie cases above"""
+    from emu.binding import compare_march
+    total = 0
+    for scene_kw, vox in ((SMALL, 0.04), (dict(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=4, radius_frac=0.0), 0.03125),
+                          (dict(width=192, height=108, room=(5.0, 4.0, 2.6), room_min=(-2.5, -2.0, -1.3), n_frames=7), 0.01)):
+        sc = synth.Scene(**scene_kw)
+        case = dict(scene={}, vpb=8, vox_size=vox, trunc=3 * vox, max_depth=3.0)
+        for steps in (100, 37):
+            p = engine_params(vh, sc, case, max_ray_steps=steps)
+            for i in range(min(sc.n_frames, 5)):
+                d, _, c2w = sc.frame(i)
+                bad, n, nonempty = compare_march(p, d, c2w)
+                assert bad == 0, f"{bad} of {n} DDA steps differ (vox {vox}, frame {i}, {steps} steps)"
+                total += nonempty
+    assert total > 50000

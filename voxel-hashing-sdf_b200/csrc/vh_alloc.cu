@@ -15,6 +15,8 @@
 //            pool slots for new blocks are popped with one atomicSub per warp (ballot/popc ranks), and blocks
 //            first seen this frame (atomicExch on the entry's frame stamp) are compacted into the visible list
 //            with one atomicAdd per warp.
+#include <cstdlib>
+
 #include "vh_engine.h"
 #include "vh_math.cuh"
 
@@ -195,9 +197,168 @@ alloc_visible_kernel(const StaticParams S, const FrameParams F, const float* __r
     if (base + i < D.list_cap) D.visible[base + i] = s_first[i];
 }
 
+// ======================================================================================================================
+// Revision 1 (opt-in: VH_ALLOC_REV=1). Same rays, same visited blocks, same insertion code — but the 3-D DDA is no
+// longer marched step by step. The reference's loop (tsdf.cu:2158-2233) keeps one crossing time per axis and advances
+// the axis with the smallest one, adding that axis's increment by repeated float addition. The k-th crossing time of an
+// axis therefore does not depend on the other axes: T_a[k] = tmax_a + tdel_a + ... (k additions) is a monotone sequence
+// that one lane can generate alone (24 lanes: 8 rays x 3 axes, a chain of K dependent FADDs each), and the loop's choice
+//     x if tx < ty && tx < tz;  else z if tz < ty;  else y
+// is "take the smallest head, ties resolved y before z before x" — a three-way MERGE of the sequences under the total
+// order (time, priority). Every element then finds its own place: element k of axis a is step
+//     pos = k + #{elements of b before it} + #{elements of c before it}
+// with the two counts taken by binary search, and those same counts are how far the ray has moved along b and c when it
+// takes that step — so the block visited at step pos is (cur0_a + k*step_a, cur0_b + n_b*step_b, cur0_c + n_c*step_c). The
+// ray ends at the first step that carries a coordinate onto its bound (an atomicMin over the three candidates). The
+// sequential march (~40 dependent instructions per step, 100 steps, ~20 us) becomes ~2 us of parallel work, and all of
+// the CTA's keys are classified and inserted in rounds of 256 instead of 200 behind a marching warp.
+// Non-finite crossing times (a pose with NaNs) cannot index out of range: positions are checked, unwritten steps stay empty.
+constexpr int ALLOC1_MAX_SMEM = 200 * 1024;
+
+__device__ __forceinline__ int axis_priority(int a) { return a == 1 ? 0 : (a == 2 ? 1 : 2); }   // ties: y, then z, then x
+
+// number of elements of the monotone sequence t[0..n) that precede the value v (ties_first: equal elements precede it too)
+__device__ __forceinline__ int merge_rank(const float* __restrict__ t, int n, float v, bool ties_first) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const float x = t[mid];
+    if (x < v || (ties_first && x == v)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// phases 0-2 for the CTA's tile of rays: skeys[step * RAYS + ray] = block visited at that step (KEY_EMPTY where the block is
+// outside the key range), s_death[ray] = last step the ray takes (K if it never reaches a bound). All threads of the CTA.
+__device__ __forceinline__ void merge_fill_keys(const StaticParams& S, const FrameParams& F, const float* __restrict__ depth, int tile_x, int tile_y,
+                                                u64* __restrict__ skeys, float* __restrict__ sT, int* __restrict__ s_death) {
+  __shared__ int s_cur[RAYS][3], s_step[RAYS][3], s_last[RAYS][3], s_alive[RAYS];
+  __shared__ float s_del[RAYS][3];
+  const int K = S.max_steps;
+  const int tid = threadIdx.x;
+
+  // phase 0: ray set-up (8 lanes), every step slot empty
+  if (tid < RAYS) {
+    RayState R;
+    ray_setup(S, F, depth, tile_x * RAYS_X + (tid & (RAYS_X - 1)), tile_y * RAYS_Y + (tid / RAYS_X), R);
+    s_alive[tid] = R.alive ? 1 : 0;
+    s_death[tid] = K;                                                 // no step ends the ray (yet)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      s_cur[tid][a] = R.cur[a]; s_step[tid][a] = R.istep[a];
+      // the a-step that carries cur_a onto bound_a is number (bound - cur) / step, counted from 1; none if the bound is not ahead
+      const long long ahead = ((long long)R.bound[a] - (long long)R.cur[a]) * (long long)R.istep[a];
+      s_last[tid][a] = (R.istep[a] != 0 && ahead >= 1 && ahead <= (long long)K) ? (int)ahead - 1 : -1;
+      sT[(tid * 3 + a) * K] = R.tmax[a];
+      s_del[tid][a] = R.tdel[a];
+    }
+  }
+  for (int i = tid; i < K * RAYS; i += (int)blockDim.x) skeys[i] = KEY_EMPTY;
+  __syncthreads();
+
+  // phase 1: the crossing times of every axis by repeated addition (tsdf.cu:2221,2226,2231), one lane per (ray, axis)
+  if (tid < RAYS * 3) {
+    float* t = sT + (size_t)tid * K;
+    float v = t[0];
+    const float del = s_del[tid / 3][tid % 3];
+    for (int k = 1; k < K; k++) { v = fadd(v, del); t[k] = v; }
+  }
+  __syncthreads();
+
+  // phase 2: every element finds its step and the block the ray is in when it takes it
+  for (int e = tid; e < RAYS * 3 * K; e += (int)blockDim.x) {
+    const int ra = e / K, k = e - ra * K, ray = ra / 3, a = ra - ray * 3;
+    if (!s_alive[ray]) continue;
+    const int b = a == 0 ? 1 : 0, c = a == 2 ? 1 : 2;                 // the other two axes
+    const float v = sT[e];
+    const int pa = axis_priority(a);
+    const int nb = merge_rank(sT + (size_t)(ray * 3 + b) * K, K, v, axis_priority(b) < pa);
+    const int nc = merge_rank(sT + (size_t)(ray * 3 + c) * K, K, v, axis_priority(c) < pa);
+    const int pos = k + nb + nc;
+    if (pos < 0 || pos >= K) continue;
+    int cur[3];
+    cur[a] = s_cur[ray][a] + k * s_step[ray][a]; cur[b] = s_cur[ray][b] + nb * s_step[ray][b]; cur[c] = s_cur[ray][c] + nc * s_step[ray][c];
+    if (key_in_range(cur[0], cur[1], cur[2])) skeys[pos * RAYS + ray] = pack_key(cur[0], cur[1], cur[2]);
+    if (k == s_last[ray][a]) atomicMin(&s_death[ray], pos);           // this step moves the ray onto its bound (tsdf.cu:2219,2224,2229)
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(ALLOC_THREADS)
+alloc_visible_kernel_r1(const StaticParams S, const FrameParams F, const float* __restrict__ depth, const DeviceView D, int tiles_x) {
+#ifdef VH_HOST_EMU
+  u64* dyn = reinterpret_cast<u64*>(emu::g_cta->dyn_smem);
+#else
+  extern __shared__ u64 dyn[];
+#endif
+  const int K = S.max_steps;
+  u64* skeys = dyn;                                                   // [K][RAYS]
+  float* sT = reinterpret_cast<float*>(dyn + (size_t)K * RAYS);       // [RAYS][3][K] crossing times
+  int* s_first = reinterpret_cast<int*>(sT + (size_t)RAYS * 3 * K);   // [K * RAYS] entries first seen this frame
+  __shared__ int s_death[RAYS];
+  __shared__ int s_cnt, s_base;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+  if (tid == 0) s_cnt = 0;
+  merge_fill_keys(S, F, depth, tile_x, tile_y, skeys, sT, s_death);
+
+  // phase 3: classify, insert, stamp and collect — the code of alloc_visible_kernel, over all K x RAYS keys
+  const float bpc = (float)S.bpc;
+  const int nkeys = K * RAYS;
+  for (int i0 = 0; i0 < nkeys; i0 += ALLOC_THREADS) {
+    const int i = i0 + tid;
+    u64 key = KEY_EMPTY;
+    if (i < nkeys && i / RAYS <= s_death[i % RAYS]) key = skeys[i];
+    if (key != KEY_EMPTY) {
+      int bx, by, bz;
+      unpack_key(key, bx, by, bz);
+      bool ok = chunk_is_candidate(S, F, block_to_chunk(bx, bpc), block_to_chunk(by, bpc), block_to_chunk(bz, bpc));   // tsdf.cu:2164
+      if (ok) ok = block_in_frustum(S, F, bx, by, bz);                                                                  // tsdf.cu:2165
+      if (ok && S.shard_count > 1) ok = owner_of_block(bx, by, bz, S.shard_count, S.shard_group) == S.shard_rank;
+      if (!ok) key = KEY_EMPTY;
+    }
+    if (__ballot_sync(0xffffffffu, key != KEY_EMPTY) != 0) {
+      const unsigned same = __match_any_sync(0xffffffffu, key);
+      const bool leader = key != KEY_EMPTY && lane == __ffs(same) - 1;
+      int entry = -1;
+      bool claimed = false;
+      if (leader) entry = map_claim(D.map, key, claimed);
+      map_assign_slots(D.map, 0xffffffffu, claimed, entry, key);
+      bool first = false;
+      if (leader && entry >= 0) first = atomicExch(&D.stamps[entry], F.frame) != F.frame;
+      const unsigned fm = __ballot_sync(0xffffffffu, first);
+      if (fm) {
+        const int l0 = __ffs(fm) - 1;
+        int base = 0;
+        if (lane == l0) base = atomicAdd(&s_cnt, __popc(fm));
+        base = __shfl_sync(0xffffffffu, base, l0);
+        if (first) s_first[base + __popc(fm & ((1u << lane) - 1))] = entry;
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  if (cnt == 0) return;
+  if (tid == 0) s_base = atomicAdd(&D.counters->visible_count, cnt);
+  __syncthreads();
+  const int base = s_base;
+  for (int i = tid; i < cnt; i += ALLOC_THREADS)
+    if (base + i < D.list_cap) D.visible[base + i] = s_first[i];
+}
+
+inline size_t alloc_r1_smem_bytes(int max_steps) {
+  return (size_t)max_steps * RAYS * sizeof(u64) + (size_t)RAYS * 3 * max_steps * sizeof(float) + (size_t)max_steps * RAYS * sizeof(int);
+}
+
 #ifndef VH_HOST_EMU
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st) {
   const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;
+  if (S.alloc_rev == 1 && alloc_r1_smem_bytes(S.max_steps) <= (size_t)ALLOC1_MAX_SMEM) {      // opt-in revision, see alloc_visible_kernel_r1
+    const size_t smem1 = alloc_r1_smem_bytes(S.max_steps);
+    if (smem1 > 48 * 1024) cudaFuncSetAttribute(alloc_visible_kernel_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    alloc_visible_kernel_r1<<<tiles_x * tiles_y, ALLOC_THREADS, smem1, st>>>(S, F, d_depth, D, tiles_x);
+    return;
+  }
   const size_t smem = 2 * CHUNK_KEYS * sizeof(u64) + (size_t)S.max_steps * RAYS * sizeof(int);
   if (smem > 48 * 1024)   // per-device attribute; only very long ray step caps get here
     cudaFuncSetAttribute(alloc_visible_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

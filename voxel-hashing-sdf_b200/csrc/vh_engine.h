@@ -42,7 +42,8 @@ struct StaticParams {
   int integrate_ctas_per_sm;      // resident 256-thread CTAs per SM the integrate kernel is compiled for (2, 3 or 4; default 4)
   uint32_t byte_bias;             // 0x4B000000 (bits of 2^23), read from the parameter block by integrate_kernel_r1's byte -> float permutes
   int integrate_rev;              // 0 (default): integrate_kernel; 1: integrate_kernel_r1 (VH_INTEGRATE_REV=1, same results, fewer instructions)
-  int pad_to_16[2];               // keeps sizeof(StaticParams) a multiple of 16: the FrameParams that follows it in every kernel's parameter
+  int alloc_rev;                  // 0 (default): alloc_visible_kernel; 1: alloc_visible_kernel_r1 (VH_ALLOC_REV=1, same visible sets, no sequential DDA)
+  int pad_to_16;                  // keeps sizeof(StaticParams) a multiple of 16: the FrameParams that follows it in every kernel's parameter
                                   // block stays 16-byte aligned, so its pose is still fetched with 128-bit constant loads
 };
 
