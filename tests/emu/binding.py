@@ -91,10 +91,10 @@ class EmuEngine:
     """pack -> allocate -> integrate -> marching cubes with the engine's kernel sources on the CPU; mirrors the subset of
     voxel-hashing-sdf_b200.TsdfEngine the parity tests use."""
 
-    def __init__(self, params, integrate_rev=0, cull=1, exact_color=0, alloc_rev=0):
+    def __init__(self, params, integrate_rev=0, cull=1, exact_color=0, alloc_rev=0, mc_rev=0):
         L = lib()
         L.emu_create.restype = C.c_void_p
-        L.emu_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.emu_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emu_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_phase_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_phase_mc.argtypes = [C.c_void_p]
@@ -109,7 +109,7 @@ class EmuEngine:
         L.emu_get_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.emu_block_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         self.L, self.params = L, params
-        self.h = L.emu_create(C.addressof(params), integrate_rev, cull, exact_color, alloc_rev)
+        self.h = L.emu_create(C.addressof(params), integrate_rev, cull, exact_color, alloc_rev, mc_rev)
         assert self.h, "emu_create rejected the parameters"
 
     def close(self):

@@ -52,6 +52,8 @@ struct McArgs { StaticParams S; uint32_t frame; DeviceView D; const int* list; c
 void run_filter_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_mesh_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 void run_filter(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
+void run_mesh_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false, 1>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
+void run_mesh_sharded_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true, 1>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 // test-only kernel: the step-by-step DDA (ray_march) and the merge formulation (merge_fill_keys) of the same tile of rays,
 // compared key by key; out[0] += mismatching steps, out[1] += steps compared, out[2] += non-empty keys
@@ -96,13 +98,14 @@ void emu_compare_march(const vh_params* p, const float* depth, const float* c2w,
   emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_march_compare, &a, smem);
 }
 
-emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exact_color, int alloc_rev) {
+emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exact_color, int alloc_rev, int mc_rev) {
   if (!p || p->voxels_per_block != VPB || p->shard_count < 1 || p->shard_count > MAX_SHARDS) return nullptr;
   emu_engine* e = new emu_engine;
   e->P = *p;
   StaticParams& S = e->S; memset(&S, 0, sizeof(S));
   derive_static_params(*p, S);
   S.verify = 0; S.integrate_ctas_per_sm = 4; S.integrate_cull = cull; S.integrate_two_steps = 0; S.integrate_rev = integrate_rev;
+  S.mc_rev = mc_rev;
   e->rev = integrate_rev; e->alloc_rev = alloc_rev; e->weight_bound_bias = exact_color ? 1u << 20 : 0u;
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket, cap = 1024;      // vh_create
   while (cap < want) cap <<= 1;
@@ -170,7 +173,8 @@ int emu_phase_mc(emu_engine* e) {
     McArgs m{S, e->F.frame, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, D.mc_queue, ctl, ctl_next, e->tables.data()};
     const bool sharded = S.shard_count > 1 && D.peers;
     emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
-    emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
+    if (S.mc_rev == 1) emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded_r1 : run_mesh_r1, &m);
+    else emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
   }
   return e->map_error | (e->engine_error << 8);
 }

@@ -12,11 +12,11 @@ from emu.binding import EmuEngine, mesh_order
 from util import CASES, engine_params, key_set, load_golden, oracle_params
 
 
-def run_pair(vh, ob, synth, scene_kw, case, frames, rev=0, alloc_rev=0, mutate=None, **eng_over):
+def run_pair(vh, ob, synth, scene_kw, case, frames, rev=0, alloc_rev=0, mc_rev=0, mutate=None, **eng_over):
     sc = synth.Scene(**scene_kw)
     color = bool(case["scene"].get("color"))
     o = ob.Oracle(oracle_params(ob, sc, case))
-    with EmuEngine(engine_params(vh, sc, case, **eng_over), integrate_rev=rev, alloc_rev=alloc_rev) as e:
+    with EmuEngine(engine_params(vh, sc, case, **eng_over), integrate_rev=rev, alloc_rev=alloc_rev, mc_rev=mc_rev) as e:
         for i in range(frames):
             d, rgb, c2w = sc.frame(i)
             if mutate is not None:
@@ -50,11 +50,11 @@ SMALL = dict(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=60, spheres=(
 CASE = dict(scene=dict(color=True), vpb=8, vox_size=0.04, trunc=0.2, max_depth=3.0)
 
 
-# kernel revisions (integrate, allocation): 0 = shipped defaults, 1 = opt-in (VH_INTEGRATE_REV=1 / VH_ALLOC_REV=1)
-@pytest.mark.parametrize("rev,alloc_rev", [(0, 0), (1, 0), (0, 1), (1, 1)])
-def test_emulated_engine_matches_oracle(vh, ob, synth, rev, alloc_rev):
-    nblocks, ntris = run_pair(vh, ob, synth, SMALL, CASE, frames=3, rev=rev, alloc_rev=alloc_rev, num_buckets=1 << 12, pool_blocks=1 << 12,
-                              tri_arena_bytes=8 << 20)
+# kernel revisions (integrate, allocation, marching cubes): 0 = shipped defaults, 1 = opt-in (VH_INTEGRATE_REV / VH_ALLOC_REV / VH_MC_REV = 1)
+@pytest.mark.parametrize("rev,alloc_rev,mc_rev", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
+def test_emulated_engine_matches_oracle(vh, ob, synth, rev, alloc_rev, mc_rev):
+    nblocks, ntris = run_pair(vh, ob, synth, SMALL, CASE, frames=3, rev=rev, alloc_rev=alloc_rev, mc_rev=mc_rev, num_buckets=1 << 12,
+                              pool_blocks=1 << 12, tri_arena_bytes=8 << 20)
     assert nblocks > 200 and ntris > 1000
 
 
@@ -98,7 +98,7 @@ def test_emulated_sharded_map_equals_single_map(vh, ob, synth, nranks, group):
         return engine_params(vh, sc, CASE, num_buckets=1 << 12, pool_blocks=1 << 12, tri_arena_bytes=8 << 20, shard_rank=rank, shard_count=n,
                              shard_group=group)
 
-    with EmuGroup(make, nranks) as g:
+    with EmuGroup(make, nranks, mc_rev=nranks - 2) as g:      # 3 ranks: with the mesh kernel's emit-pass revision
         for i in range(3):
             d, rgb, c2w = sc.frame(i)
             o.process_frame(d, rgb, c2w)

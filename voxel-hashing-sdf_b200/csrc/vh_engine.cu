@@ -147,7 +147,8 @@ int vh_create(const vh_params* p, vh_engine** out) {
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_ALLOC_REV"); S.alloc_rev = (v && v[0] == '1') ? 1 : 0; }
-  S.pad_to_16 = 0;
+  { const char* v = getenv("VH_MC_REV"); S.mc_rev = (v && v[0] == '1') ? 1 : 0; }
+  static_assert(sizeof(StaticParams) % 16 == 0, "keep the FrameParams behind StaticParams 16-byte aligned in the kernels' parameter blocks");
 
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket;
   uint64_t cap = 1024;

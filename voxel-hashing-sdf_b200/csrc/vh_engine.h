@@ -43,8 +43,9 @@ struct StaticParams {
   uint32_t byte_bias;             // 0x4B000000 (bits of 2^23), read from the parameter block by integrate_kernel_r1's byte -> float permutes
   int integrate_rev;              // 0 (default): integrate_kernel; 1: integrate_kernel_r1 (VH_INTEGRATE_REV=1, same results, fewer instructions)
   int alloc_rev;                  // 0 (default): alloc_visible_kernel; 1: alloc_visible_kernel_r1 (VH_ALLOC_REV=1, same visible sets, no sequential DDA)
-  int pad_to_16;                  // keeps sizeof(StaticParams) a multiple of 16: the FrameParams that follows it in every kernel's parameter
-                                  // block stays 16-byte aligned, so its pose is still fetched with 128-bit constant loads
+  int mc_rev;                     // 0 (default); 1: the mesh kernel's emit pass issues a triangle's six colour gathers before interpolating (VH_MC_REV=1)
+  // sizeof(StaticParams) stays a multiple of 16: the FrameParams that follows it in every kernel's parameter block keeps its
+  // 16-byte alignment, so its pose is still fetched with 128-bit constant loads (add fields four ints at a time)
 };
 
 struct FrameParams {

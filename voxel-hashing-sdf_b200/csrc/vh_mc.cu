@@ -123,6 +123,40 @@ __device__ __forceinline__ Vtx edge_vertex(const McBlock& B, const DeviceView& D
   return vertex_interp(pa, pb, B.tile[(ax * TILE + ay) * TILE + az], B.tile[(qx * TILE + qy) * TILE + qz], color);
 }
 
+// Revision 1 of the emit pass (opt-in: VH_MC_REV=1) splits edge_vertex in two so that the six colour gathers of a triangle
+// are all in flight before the first interpolation consumes one (the mesh kernel's stall samples sit on the unpacking of
+// a colour loaded two instructions earlier, one vertex at a time). Same operations, same results.
+struct EdgeFetch { int a_pos, b_pos; float va, vb; uint32_t ca, cb; };   // positions packed x | y << 8 | z << 16 (tile coordinates 0..8)
+template <bool SHARDED>
+__device__ __forceinline__ EdgeFetch edge_fetch(const McBlock& B, const DeviceView& D, int lx, int ly, int lz, int e, bool color) {
+  const int a = e < 8 ? e : e - 8;
+  const int b = e < 4 ? ((e + 1) & 3) : (e < 8 ? 4 + ((e - 3) & 3) : e - 4);
+  const int ax = lx + corner_ox(a), ay = ly + corner_oy(a), az = lz + corner_oz(a);
+  const int qx = lx + corner_ox(b), qy = ly + corner_oy(b), qz = lz + corner_oz(b);
+  EdgeFetch f;
+  f.a_pos = ax | (ay << 8) | (az << 16); f.b_pos = qx | (qy << 8) | (qz << 16);
+  f.ca = 0; f.cb = 0;
+  if (color) {
+    const int ma = (ax >> 3) | ((ay >> 3) << 1) | ((az >> 3) << 2), mb = (qx >> 3) | ((qy >> 3) << 1) | ((qz >> 3) << 2);
+    const int sa = B.nb_slot[ma], sb = B.nb_slot[mb];
+    const uchar4* rgb_a = SHARDED ? D.peers->v[B.nb_owner[ma]].rgb : D.rgb;
+    const uchar4* rgb_b = SHARDED ? D.peers->v[B.nb_owner[mb]].rgb : D.rgb;
+    const uchar4 ca = rgb_a[(size_t)sa * BLOCK_VOX + ((ax & 7) * 64 + (ay & 7) * 8 + (az & 7))];
+    const uchar4 cb = rgb_b[(size_t)sb * BLOCK_VOX + ((qx & 7) * 64 + (qy & 7) * 8 + (qz & 7))];
+    f.ca = (uint32_t)ca.x | ((uint32_t)ca.y << 8) | ((uint32_t)ca.z << 16);
+    f.cb = (uint32_t)cb.x | ((uint32_t)cb.y << 8) | ((uint32_t)cb.z << 16);
+  }
+  f.va = B.tile[(ax * TILE + ay) * TILE + az]; f.vb = B.tile[(qx * TILE + qy) * TILE + qz];
+  return f;
+}
+__device__ __forceinline__ Vtx edge_finish(const McBlock& B, const EdgeFetch& f, bool color) {
+  Vtx pa, pb;
+  pa.x = i2f(B.bx * VPB + (f.a_pos & 0xFF)); pa.y = i2f(B.by * VPB + ((f.a_pos >> 8) & 0xFF)); pa.z = i2f(B.bz * VPB + (f.a_pos >> 16));
+  pb.x = i2f(B.bx * VPB + (f.b_pos & 0xFF)); pb.y = i2f(B.by * VPB + ((f.b_pos >> 8) & 0xFF)); pb.z = i2f(B.bz * VPB + (f.b_pos >> 16));
+  pa.c = f.ca; pb.c = f.cb;
+  return vertex_interp(pa, pb, f.va, f.vb, color);
+}
+
 __device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int lz) {
   int cube = 0;
 #pragma unroll
@@ -133,7 +167,7 @@ __device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int
 
 // Mesh one block with the whole warp: stage the 9^3 tile, pass 1 lists candidate triangles, pass 2 writes the survivors.
 // B.nb_slot[0..8) holds the pool slots of the block and its seven upper neighbours (-1 = absent), `present` the same as bits.
-template <bool SHARDED>
+template <bool SHARDED, int REV>
 __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D, const int slot, const unsigned present, const int (&halo)[7],
                                           float* tile, unsigned short* wlist, const signed char* s_tri, const unsigned char* s_ntri,
                                           const bool color, unsigned long long* __restrict__ out_offset, int* __restrict__ out_count,
@@ -226,9 +260,15 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
           const int t = item >> 3, k = item & 7;
           const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
           const signed char* row = s_tri + cube_index(tile, lx, ly, lz) * 16 + 3 * k;
+          if (REV == 1) {
+            const EdgeFetch f0 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[0], color), f1 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[1], color),
+                            f2 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[2], color);
+            p0 = edge_finish(B, f0, color); p1 = edge_finish(B, f1, color); p2 = edge_finish(B, f2, color);
+          } else {
           p0 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[0], color);
           p1 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[1], color);
           p2 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[2], color);
+          }
           valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -317,7 +357,7 @@ mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D,
 // Persistent warps pull blocks off the work queue (one atomicAdd per block) and mesh them: perfect balance whatever the
 // spatial clustering of surface blocks. The last thing the kernel does is clear the OTHER queue-control slot, which the
 // next launch pair will use (the two slots alternate, so no memset node is needed per frame).
-template <bool SHARDED>
+template <bool SHARDED, int REV = 0>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int full_map, unsigned long long* __restrict__ out_offset,
                int* __restrict__ out_count, const McWork* __restrict__ queue, McQueueCtl* __restrict__ ctl, McQueueCtl* __restrict__ ctl_next,
@@ -368,7 +408,7 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
     __syncwarp();                              // previous block's readers of s_nb / tile / list are done
     if (lane < 8) { s_nb[wid][lane] = w->nb[lane]; s_nbo[wid][lane] = SHARDED ? (int)w->owner[lane] : 0; }
     __syncwarp();
-    my_tris += (unsigned long long)mesh_block<SHARDED>(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
+    my_tris += (unsigned long long)mesh_block<SHARDED, REV>(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
@@ -389,10 +429,12 @@ void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const De
   const int mgrid = num_sms * mesh_ctas;         // 5 CTAs of 4 warps fit an SM (36.7 KB of shared memory each)
   if (S.shard_count > 1 && D.peers) {
     mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    if (S.mc_rev == 1) mc_mesh_kernel<true, 1><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    else mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
   } else {
     mc_filter_kernel<false><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    if (S.mc_rev == 1) mc_mesh_kernel<false, 1><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    else mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
   }
 }
 #endif  // !VH_HOST_EMU
