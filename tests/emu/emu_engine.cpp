@@ -51,6 +51,8 @@ struct McArgs { StaticParams S; uint32_t frame; DeviceView D; const int* list; c
                 McWork* queue; McQueueCtl* ctl; McQueueCtl* ctl_next; const uint4* tables; };
 void run_filter_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_mesh_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
+void run_filter_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false, 1>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
+void run_filter_sharded_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true, 1>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_filter(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_mesh_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false, 1>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 void run_mesh_sharded_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true, 1>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
@@ -172,7 +174,8 @@ int emu_phase_mc(emu_engine* e) {
     e->mc_parity ^= 1;
     McArgs m{S, e->F.frame, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, D.mc_queue, ctl, ctl_next, e->tables.data()};
     const bool sharded = S.shard_count > 1 && D.peers;
-    emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
+    if (S.mc_rev == 1) emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded_r1 : run_filter_r1, &m);
+    else emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
     if (S.mc_rev == 1) emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded_r1 : run_mesh_r1, &m);
     else emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
   }

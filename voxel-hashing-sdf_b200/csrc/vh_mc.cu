@@ -293,7 +293,11 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
 // room scan most of the working set is free space, so most blocks end here without their voxels being read. Survivors
 // are appended to a work queue (block, slot, the eight corner-block slots and owners), which decouples meshing from the
 // list order: surface blocks are clustered in the list, and a warp that drew four of them used to serialise them.
-template <bool SHARDED>
+// REV 1 (opt-in, VH_MC_REV=1): the neighbour look-up reads key, stamp and slot of the FIRST probe position together (three
+// independent loads; at the table's load factor nine look-ups in ten end there) instead of key -> stamp/slot one after
+// the other, which shortens the chain of dependent loads the filter spends its time waiting on. Later probe positions
+// (rare) take the ordinary path. Same results.
+template <bool SHARDED, int REV = 0>
 __global__ void __launch_bounds__(256)
 mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int* __restrict__ list,
                  const int* __restrict__ list_count, const int full_map, unsigned long long* __restrict__ out_offset,
@@ -319,15 +323,25 @@ mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D,
       const int nx = bx + (sub & 1), ny = by + ((sub >> 1) & 1), nz = bz + ((sub >> 2) & 1);
       if (key_in_range(nx, ny, nz)) {
         const u64 nk = pack_key(nx, ny, nz);
+        const u64* t_keys = D.map.keys; const int* t_slots = D.map.slots; const uint32_t* t_stamps = D.stamps; const int* t_neg = D.neg_count;
+        uint32_t t_mask = D.map.mask;
         if (SHARDED) {
           // the neighbour lives on the GPU its key hashes to: probe that GPU's table and read its stamp / counter over NVLink
           nb_owner = (int)owner_of_block(nx, ny, nz, S.shard_count, S.shard_group);
           const PeerView P = D.peers->v[nb_owner];
-          const int e = map_find_in(P.keys, P.mask, nk);
-          if (e >= 0 && (full_map || P.stamps[e] == frame)) { nb = P.slots[e]; if (nb >= 0) nneg = P.neg_count[nb]; }
+          t_keys = P.keys; t_slots = P.slots; t_stamps = P.stamps; t_neg = P.neg_count; t_mask = P.mask;
+        }
+        if (REV == 1) {
+          const uint32_t h0 = hash_key(nk) & t_mask;
+          const u64 k0 = __ldcg(&t_keys[h0]);
+          uint32_t st = t_stamps[h0];
+          int sl = t_slots[h0];
+          int e = k0 == nk ? (int)h0 : -1;
+          if (k0 != nk && k0 != KEY_EMPTY) { e = map_find_in(t_keys, t_mask, nk); if (e >= 0) { st = t_stamps[e]; sl = t_slots[e]; } }
+          if (e >= 0 && (full_map || st == frame)) { nb = sl; if (nb >= 0) nneg = t_neg[nb]; }
         } else {
-          const int e = map_find(D.map, nk);
-          if (e >= 0 && (full_map || D.stamps[e] == frame)) { nb = D.map.slots[e]; if (nb >= 0) nneg = D.neg_count[nb]; }
+          const int e = map_find_in(t_keys, t_mask, nk);
+          if (e >= 0 && (full_map || t_stamps[e] == frame)) { nb = t_slots[e]; if (nb >= 0) nneg = t_neg[nb]; }
         }
       }
     }
@@ -428,11 +442,13 @@ void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const De
   const int fgrid = num_sms * filter_ctas;
   const int mgrid = num_sms * mesh_ctas;         // 5 CTAs of 4 warps fit an SM (36.7 KB of shared memory each)
   if (S.shard_count > 1 && D.peers) {
-    mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    if (S.mc_rev == 1) mc_filter_kernel<true, 1><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    else mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
     if (S.mc_rev == 1) mc_mesh_kernel<true, 1><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
     else mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
   } else {
-    mc_filter_kernel<false><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    if (S.mc_rev == 1) mc_filter_kernel<false, 1><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    else mc_filter_kernel<false><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
     if (S.mc_rev == 1) mc_mesh_kernel<false, 1><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
     else mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
   }
