@@ -77,6 +77,8 @@ def config_dict(args, cfg, sc, world):
         "color": not args.no_color,
         "multi_gpu": "one independent sequence+map per GPU (config 5 style), no collective on the data path" if world > 1 else "single map",
         "l2": "inputs larger than L2: every frame is a distinct 1.2 MB depth (+0.9 MB rgb) image and touches a ~280 MB voxel working set (L2 = 126 MB)",
+        # run-time switches in effect; empty = the shipped defaults
+        "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("VH_") and k != "VH_TEST_REV1"},
     }
 
 
@@ -391,7 +393,7 @@ def run_ours(args):
                       "triangles": tris_per_frame,
                       "ms_alloc": ms_alloc, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated,
                       "arena_compactions_in_500_frames": int(st_last.arena_compactions)},
-        "roofline": {"kernel": "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "roofline": {"kernel": "vh::integrate_kernel_r1" if os.environ.get("VH_INTEGRATE_REV") == "1" else "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int},
         "roofline_mc": {"kernel": "vh::mc_filter_kernel + vh::mc_mesh_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
