@@ -214,3 +214,52 @@ def test_emulated_dda_merge_equals_step_by_step_march(vh, synth):
                 assert bad == 0, f"{bad} of {n} DDA steps differ (vox {vox}, frame {i}, {steps} steps)"
                 total += nonempty
     assert total > 50000
+
+
+def _random_pose_scene(synth, seed, **kw):
+    """a Scene whose poses are random rigid motions (any pitch / roll / yaw, anywhere in the room) instead of the horizontal
+    circle: projections with all nine rotation entries non-trivial, blocks that straddle the camera plane, views of the
+    floor and the ceiling"""
+    rng = np.random.RandomState(seed)
+
+    class RandomPoses(synth.Scene):
+        def pose(self, i):
+            r = np.random.RandomState(seed * 1000 + i)
+            q = r.normal(size=4); q /= np.linalg.norm(q)
+            w, x, y, z = q
+            rot = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                            [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            lo = np.array(self.room_min); ext = np.array(self.room)
+            pos = lo + ext * (0.25 + 0.5 * r.random_sample(3))
+            m = np.eye(4); m[:3, :3] = rot; m[:3, 3] = pos
+            return m.astype(np.float32).reshape(16)
+
+    del rng
+    return RandomPoses(**kw)
+
+
+@pytest.mark.parametrize("seed,revs", [(1, (0, 0, 0)), (2, (1, 1, 1)), (3, (1, 1, 1)), (4, (1, 0, 1)), (5, (0, 1, 0))])
+def test_emulated_engine_random_rigid_poses(vh, ob, synth, seed, revs):
+    """odd image size (not a multiple of the 16-pixel tiles or the 10-pixel ray stride), off-centre principal point,
+    random rigid poses; three frames that overlap only by chance"""
+    sc = _random_pose_scene(synth, seed, width=150, height=113, room=(3.0, 2.6, 2.2), room_min=(-1.2, -0.9, -0.4), n_frames=8, color=True, holes=0.03)
+    sc.cx, sc.cy = 71.3, 59.8
+    case = dict(scene=dict(color=True), vpb=8, vox_size=0.025, trunc=0.08, max_depth=2.5)
+    o = ob.Oracle(oracle_params(ob, sc, case))
+    with EmuEngine(engine_params(vh, sc, case, num_buckets=1 << 13, pool_blocks=1 << 13, tri_arena_bytes=16 << 20), integrate_rev=revs[0], alloc_rev=revs[1],
+                   mc_rev=revs[2]) as e:
+        for i in range(3):
+            d, rgb, c2w = sc.frame(i)
+            o.process_frame(d, rgb, c2w)
+            e.process_frame(d, rgb, c2w)
+            assert key_set(e.visible_keys()) == key_set(o.visible_keys()), f"visible set differs in frame {i}"
+            assert e.last_updates == o.last_updates and e.last_triangles == o.last_triangles, f"frame {i}"
+        keys = o.all_keys()
+        so, wo, co, _ = o.get_blocks(keys)
+        se, we, ce, found, neg = e.get_blocks(keys)
+        assert found.all() and np.array_equal(se.view(np.uint32), so.view(np.uint32)) and np.array_equal(we, wo) and np.array_equal(ce, co)
+        xyz_o, rgb_o = o.triangles()
+        xyz_e, rgb_e = e.block_triangles(mesh_order(keys))
+        assert xyz_e.shape == xyz_o.shape and np.array_equal(xyz_e.view(np.uint32), xyz_o.view(np.uint32)) and np.array_equal(rgb_e, rgb_o)
+        assert len(keys) > 100
