@@ -130,6 +130,12 @@ class Oracle:
     def stage_mc(self):
         return self.L.vo_stage_mc(self.h)
 
+    def full_map_mc(self):
+        """meshes every allocated block against the whole map (replaces the per-frame meshes: call it last); returns the triangle count"""
+        self.L.vo_full_map_mc.restype = C.c_longlong
+        self.L.vo_full_map_mc.argtypes = [C.c_void_p]
+        return self.L.vo_full_map_mc(self.h)
+
     @property
     def num_visible(self):
         return self.L.vo_num_visible(self.h)

@@ -471,6 +471,16 @@ long long vo_stage_mc(vo_oracle* o) {
   o->last_tris = t; return t;
 }
 
+/* Full-map extraction (no reference counterpart: the reference only ever meshes a frame's working set). Every allocated
+ * block is meshed with the working-set rule applied to the whole map: a corner counts if its block is allocated at all.
+ * Implemented as "a frame whose working set is every block"; it replaces the per-block meshes kept so far, so call it last. */
+long long vo_full_map_mc(vo_oracle* o) {
+  o->frame++;
+  o->nvisible = 0;
+  for (size_t b = 0; b < o->nblocks; b++) mark_visible(o, o->blocks[b].key.x, o->blocks[b].key.y, o->blocks[b].key.z);
+  return vo_stage_mc(o);
+}
+
 int vo_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -107,7 +107,9 @@ class EmuEngine:
         L.emu_visible_keys.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_all_keys.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_get_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
-        L.emu_block_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.emu_block_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_full_map_mc.restype = C.c_longlong
+        L.emu_full_map_mc.argtypes = [C.c_void_p]
         self.L, self.params = L, params
         self.h = L.emu_create(C.addressof(params), integrate_rev, cull, exact_color, alloc_rev, mc_rev)
         assert self.h, "emu_create rejected the parameters"
@@ -166,11 +168,18 @@ class EmuEngine:
         self.L.emu_get_blocks(self.h, keys.ctypes.data, n, sdf.ctypes.data, w.ctypes.data, rgb.ctypes.data, found.ctypes.data, neg.ctypes.data)
         return sdf, w, rgb, found.astype(bool), neg
 
-    def block_triangles(self, keys):
+    def full_map_mc(self):
+        """vh_extract_mesh(VH_MESH_FULL_MAP): every allocated block meshed against the whole map; returns the triangle count"""
+        n = self.L.emu_full_map_mc(self.h)
+        assert n >= 0, "triangle arena overflow"
+        return n
+
+    def block_triangles(self, keys, full_map=False):
         keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
-        n = self.L.emu_block_triangles(self.h, keys.ctypes.data, len(keys), None, None)
+        n = self.L.emu_block_triangles(self.h, keys.ctypes.data, len(keys), None, None, int(full_map))
+        assert n >= 0
         xyz = np.zeros((max(n, 1), 3, 3), np.float32); rgb = np.zeros((max(n, 1), 3, 3), np.uint8)
-        self.L.emu_block_triangles(self.h, keys.ctypes.data, len(keys), xyz.ctypes.data, rgb.ctypes.data)
+        self.L.emu_block_triangles(self.h, keys.ctypes.data, len(keys), xyz.ctypes.data, rgb.ctypes.data, int(full_map))
         return xyz[:n], rgb[:n]
 
 

@@ -40,6 +40,9 @@ struct emu_engine {
   uint64_t frames = 0;
   uint32_t integrate_launches = 0, weight_bound_bias = 0;
   int rev = 0, alloc_rev = 0;
+  std::vector<int> full_list, full_cnt;          // full-map extraction (emu_full_map_mc)
+  std::vector<unsigned long long> full_off;
+  int full_valid = 0;
   PeerTable peers;               // multi-GPU emulation: every shard's tables and planes (plain host pointers here)
 };
 
@@ -187,6 +190,31 @@ int emu_process_frame(emu_engine* e, const float* depth, const uint8_t* rgb, con
   return rc | emu_phase_mc(e);
 }
 
+// vh_extract_mesh(VH_MESH_FULL_MAP): list every allocated block (list_all_blocks_kernel), then the two marching-cubes kernels with
+// full_map = 1 into separate offset/count arrays (the per-frame meshes stay). Returns the triangle count.
+struct ListArgs { DeviceView D; int* list; int* list_count; };
+static void run_list_all(void* p) { ListArgs* a = static_cast<ListArgs*>(p); list_all_blocks_kernel(a->D, a->list, a->list_count); }
+
+long long emu_full_map_mc(emu_engine* e) {
+  const StaticParams& S = e->S; DeviceView& D = e->D;
+  const int nb = D.map.num_blocks;
+  e->full_list.assign(nb, 0); e->full_off.assign(nb, 0); e->full_cnt.assign(nb, 0);
+  int count = 0;
+  ListArgs la{D, e->full_list.data(), &count};
+  emu::run_grid(dim3((nb + 255) / 256), dim3(256), run_list_all, &la);
+  McQueueCtl* ctl = D.mc_ctl + (e->mc_parity & 1);
+  McQueueCtl* ctl_next = D.mc_ctl + ((e->mc_parity & 1) ^ 1);
+  e->mc_parity ^= 1;
+  McArgs m{S, e->F.frame, D, e->full_list.data(), &count, 1, e->full_off.data(), e->full_cnt.data(), D.mc_queue, ctl, ctl_next, e->tables.data()};
+  const bool sharded = S.shard_count > 1 && D.peers;
+  if (S.mc_rev == 1) { emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded_r1 : run_filter_r1, &m); emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded_r1 : run_mesh_r1, &m); }
+  else { emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m); emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m); }
+  long long t = 0;
+  for (int i = 0; i < nb; i++) t += e->full_cnt[i];
+  e->full_valid = 1;
+  return (e->engine_error & 1) ? -1 : t;
+}
+
 // vh_shard_connect: every rank gets a view of every rank's table and planes (CUDA-IPC mappings on the GPU, pointers here)
 int emu_connect(emu_engine** ranks, int n) {
   if (n < 1 || n > MAX_SHARDS) return -1;
@@ -232,14 +260,17 @@ void emu_get_blocks(const emu_engine* e, const int* keys_xyz, int n, float* sdf,
   }
 }
 // stored triangles of the given blocks, concatenated in the given order: returns the count; xyz [T][3][3], rgb [T][3][3] (may be null to count)
-long long emu_block_triangles(const emu_engine* e, const int* keys_xyz, int n, float* xyz, uint8_t* rgb) {
+long long emu_block_triangles(const emu_engine* e, const int* keys_xyz, int n, float* xyz, uint8_t* rgb, int full_map) {
   long long t = 0;
+  if (full_map && !e->full_valid) return -1;
   for (int i = 0; i < n; i++) {
     const int s = find_slot(e, keys_xyz[3 * i], keys_xyz[3 * i + 1], keys_xyz[3 * i + 2]);
     if (s < 0) continue;
-    for (int k = 0; k < e->tri_count[s]; k++, t++) {
+    const int cnt = full_map ? e->full_cnt[s] : e->tri_count[s];
+    const unsigned long long off = full_map ? e->full_off[s] : e->tri_offset[s];
+    for (int k = 0; k < cnt; k++, t++) {
       if (!xyz) continue;
-      const vh_triangle& T = e->arena[e->tri_offset[s] + k];
+      const vh_triangle& T = e->arena[off + k];
       for (int v = 0; v < 3; v++) {
         xyz[(t * 3 + v) * 3 + 0] = T.p[v].x; xyz[(t * 3 + v) * 3 + 1] = T.p[v].y; xyz[(t * 3 + v) * 3 + 2] = T.p[v].z;
         rgb[(t * 3 + v) * 3 + 0] = T.p[v].r; rgb[(t * 3 + v) * 3 + 1] = T.p[v].g; rgb[(t * 3 + v) * 3 + 2] = T.p[v].b;

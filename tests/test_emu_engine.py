@@ -263,3 +263,27 @@ def test_emulated_engine_random_rigid_poses(vh, ob, synth, seed, revs):
         xyz_e, rgb_e = e.block_triangles(mesh_order(keys))
         assert xyz_e.shape == xyz_o.shape and np.array_equal(xyz_e.view(np.uint32), xyz_o.view(np.uint32)) and np.array_equal(rgb_e, rgb_o)
         assert len(keys) > 100
+
+
+@pytest.mark.parametrize("mc_rev", [0, 1])
+def test_emulated_full_map_extraction(vh, ob, synth, mc_rev):
+    """VH_MESH_FULL_MAP: every allocated block re-meshed against the whole map (a corner counts if its block is allocated at
+    all) — list_all_blocks_kernel + both marching-cubes kernels with full_map = 1 — against the oracle's full-map pass;
+    the per-frame meshes are untouched by it and it yields at least as many triangles"""
+    sc = synth.Scene(**SMALL)
+    o = ob.Oracle(oracle_params(ob, sc, CASE))
+    with EmuEngine(engine_params(vh, sc, CASE, num_buckets=1 << 12, pool_blocks=1 << 12, tri_arena_bytes=16 << 20), mc_rev=mc_rev) as e:
+        for i in (0, 6, 12):                      # views that overlap only partly: blocks whose neighbours were not in their frame's working set
+            d, rgb, c2w = sc.frame(i)
+            o.process_frame(d, rgb, c2w)
+            e.process_frame(d, rgb, c2w)
+        keys = mesh_order(o.all_keys())
+        ref_xyz, ref_rgb = o.triangles()
+        n_full = e.full_map_mc()
+        per_frame_xyz, per_frame_rgb = e.block_triangles(keys)
+        assert np.array_equal(per_frame_xyz, ref_xyz) and np.array_equal(per_frame_rgb, ref_rgb), "full-map extraction disturbed the per-frame meshes"
+        assert o.full_map_mc() == n_full
+        full_xyz_o, full_rgb_o = o.triangles()
+        full_xyz, full_rgb = e.block_triangles(keys, full_map=True)
+        assert full_xyz.shape == full_xyz_o.shape and np.array_equal(full_xyz.view(np.uint32), full_xyz_o.view(np.uint32)) and np.array_equal(full_rgb, full_rgb_o)
+        assert n_full > len(ref_xyz) > 0
