@@ -27,6 +27,7 @@
 #include <mutex>
 #include <string>
 #include <utility>
+#include <unordered_map>
 #include <vector>
 
 #include "vh_c.h"
@@ -243,6 +244,53 @@ class GpuTsdfGenerator {
     return -1;
   }
 
+  // ---- host chunk store (optional tier for maps beyond one GPU) -----------------------------------------------------
+  // The reference runs these two every frame because its map lives on the host (tsdf.cu:277-457, :469-596). Here the map is
+  // resident and processFrame never calls them; a caller who needs the tier calls them around processFrame with the frame's
+  // pose: blocks whose chunk leaves the reference's residency region go to host_store_, stored blocks whose chunk enters
+  // it come back. Voxels only: the per-frame meshes of streamed-out blocks are dropped (SetMeshMode(VH_MESH_FULL_MAP)
+  // re-meshes what is on the device).
+  void streamOutGPU2CPU(float* c2w) {
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    int n = 0;
+    raise(vh_far_blocks(engine_, c2w, nullptr, 0, &n));
+    if (n <= 0) return;
+    std::vector<int32_t> keys((size_t)n * 3);
+    raise(vh_far_blocks(engine_, c2w, keys.data(), n, &n));
+    std::vector<float> sdf((size_t)n * 512), w((size_t)n * 512);
+    std::vector<uint8_t> rgb((size_t)n * 512 * 3), found((size_t)n);
+    raise(vh_evict_blocks(engine_, keys.data(), n, sdf.data(), w.data(), rgb.data(), found.data()));
+    for (int i = 0; i < n; i++) {
+      if (!found[(size_t)i]) continue;
+      HostBlock& b = host_store_[StoreKey{keys[3 * (size_t)i], keys[3 * (size_t)i + 1], keys[3 * (size_t)i + 2]}];
+      b.sdf.assign(sdf.begin() + (size_t)i * 512, sdf.begin() + (size_t)(i + 1) * 512);
+      b.weight.assign(w.begin() + (size_t)i * 512, w.begin() + (size_t)(i + 1) * 512);
+      b.rgb.assign(rgb.begin() + (size_t)i * 1536, rgb.begin() + (size_t)(i + 1) * 1536);
+    }
+  }
+  void streamInCPU2GPU(float* c2w) {
+    std::unique_lock<std::mutex> lock(tsdf_mutex_);
+    if (host_store_.empty()) return;
+    std::vector<int32_t> keys;
+    keys.reserve(host_store_.size() * 3);
+    for (const auto& kv : host_store_) { keys.push_back(kv.first.x); keys.push_back(kv.first.y); keys.push_back(kv.first.z); }
+    const int n = (int)host_store_.size();
+    std::vector<uint8_t> in((size_t)n);
+    raise(vh_blocks_resident(&params_, c2w, keys.data(), n, in.data()));
+    std::vector<int32_t> up; std::vector<float> sdf, w; std::vector<uint8_t> rgb;
+    for (int i = 0; i < n; i++) {
+      if (!in[(size_t)i]) continue;
+      const StoreKey k{keys[3 * (size_t)i], keys[3 * (size_t)i + 1], keys[3 * (size_t)i + 2]};
+      const HostBlock& b = host_store_[k];
+      up.insert(up.end(), {k.x, k.y, k.z});
+      sdf.insert(sdf.end(), b.sdf.begin(), b.sdf.end()); w.insert(w.end(), b.weight.begin(), b.weight.end()); rgb.insert(rgb.end(), b.rgb.begin(), b.rgb.end());
+    }
+    if (up.empty()) return;
+    raise(vh_upload_blocks(engine_, up.data(), (int)(up.size() / 3), sdf.data(), w.data(), rgb.data()));
+    for (size_t i = 0; i < up.size(); i += 3) host_store_.erase(StoreKey{up[i], up[i + 1], up[i + 2]});
+  }
+  size_t hostStoreBlocks() const { return host_store_.size(); }
+
   // engine-level extras
   vh_engine* handle() const { return engine_; }
   vh_stats stats() { vh_stats s; raise(vh_get_stats(engine_, &s)); return s; }
@@ -256,6 +304,11 @@ class GpuTsdfGenerator {
     if (rc == VH_ERR_TABLE_FULL) throw "Error here!";
     throw "CUDA Error";
   }
+
+  struct StoreKey { int32_t x, y, z; bool operator==(const StoreKey& o) const { return x == o.x && y == o.y && z == o.z; } };
+  struct StoreHash { size_t operator()(const StoreKey& k) const { return (size_t)k.x * 73856093u ^ (size_t)k.y * 19349669u ^ (size_t)k.z * 83492791u; } };   // BlockHasher, tsdf.cuh:141-148
+  struct HostBlock { std::vector<float> sdf, weight; std::vector<uint8_t> rgb; };
+  std::unordered_map<StoreKey, HostBlock, StoreHash> host_store_;
 
   vh_engine* engine_ = nullptr;
   vh_params params_;

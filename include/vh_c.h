@@ -171,6 +171,22 @@ VH_API int vh_shard_stats(vh_engine* e, vh_stats* sum);
 /* host-only helper of the gather: merge per-shard block lists (each in mesh order) into the global mesh order */
 VH_API int vh_mesh_order_merge(int n_parts, const int32_t* const* keys_xyz, const int* nblocks, int blocks_per_chunk, int32_t* out_part, int32_t* out_index);
 
+/* ---- out-of-core tier (optional; call between frames, single-GPU maps) -------------------------------------------------
+ * The reference keeps its map on the host and streams it through the GPU every frame (streamInCPU2GPU tsdf.cu:277-457,
+ * streamOutGPU2CPU :469-596). Here the map is resident; these three calls move whole blocks for scenes beyond one GPU.
+ * vh_far_blocks: allocated blocks whose chunk fails the reference's residency rule for pose c2w (chunk cube + chunk sphere
+ *   around the frustum centre, tsdf.cu:166-187,300-312); *n = how many there are (may exceed cap), keys sorted.
+ * vh_evict_blocks: like vh_download_blocks, then the blocks leave the map (entries, pool slots, stored triangles).
+ * vh_upload_blocks: inserts the blocks with these voxels (an existing block is overwritten); rgb may be NULL (zeros).
+ * The per-frame meshes of evicted blocks are dropped; blocks that come back have none until a frame sees them again
+ * (VH_MESH_FULL_MAP re-meshes everything that is on the device). */
+VH_API int vh_far_blocks(vh_engine* e, const float* c2w, int32_t* out_xyz, int cap, int* n);
+/* the same rule for blocks that are in the caller's store, not on the device (host arithmetic only, no engine): out[i] = 1 if
+ * block i belongs on the device for pose c2w — what streamInCPU2GPU would upload */
+VH_API int vh_blocks_resident(const vh_params* p, const float* c2w, const int32_t* keys_xyz, int n, uint8_t* out);
+VH_API int vh_evict_blocks(vh_engine* e, const int32_t* keys_xyz, int n, float* sdf, float* weight, uint8_t* rgb, uint8_t* found);
+VH_API int vh_upload_blocks(vh_engine* e, const int32_t* keys_xyz, int n, const float* sdf, const float* weight, const uint8_t* rgb);
+
 /* pinned host memory helpers for callers that want DMA-able frame buffers */
 VH_API int vh_host_alloc(void** p, size_t bytes);
 VH_API int vh_host_free(void* p);

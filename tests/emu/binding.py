@@ -102,7 +102,7 @@ class EmuEngine:
         L.emu_last_updates.restype = C.c_ulonglong
         L.emu_last_triangles.restype = C.c_ulonglong
         L.emu_block_triangles.restype = C.c_longlong
-        for f in ("emu_destroy", "emu_num_visible", "emu_last_updates", "emu_last_triangles", "emu_num_blocks"):
+        for f in ("emu_destroy", "emu_num_visible", "emu_last_updates", "emu_last_triangles", "emu_num_blocks", "emu_free_slots"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.emu_visible_keys.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_all_keys.argtypes = [C.c_void_p, C.c_void_p]
@@ -167,6 +167,40 @@ class EmuEngine:
         found = np.zeros(n, np.uint8); neg = np.zeros(n, np.int32)
         self.L.emu_get_blocks(self.h, keys.ctypes.data, n, sdf.ctypes.data, w.ctypes.data, rgb.ctypes.data, found.ctypes.data, neg.ctypes.data)
         return sdf, w, rgb, found.astype(bool), neg
+
+    # -- out-of-core tier (csrc/vh_stream.cu) -----------------------------------------------------
+    def far_blocks(self, c2w):
+        c2w = np.ascontiguousarray(c2w, np.float32)
+        self.L.emu_far_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        n = self.L.emu_far_blocks(self.h, c2w.ctypes.data, None, 0)
+        out = np.zeros((max(n, 1), 3), np.int32)
+        self.L.emu_far_blocks(self.h, c2w.ctypes.data, out.ctypes.data, n)
+        return out[:n]
+
+    def evict_blocks(self, keys):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        n = len(keys)
+        sdf = np.zeros((n, 512), np.float32); w = np.zeros((n, 512), np.float32); rgb = np.zeros((n, 512, 3), np.uint8)
+        found = np.zeros(n, np.uint8)
+        self.L.emu_evict_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        released = self.L.emu_evict_blocks(self.h, keys.ctypes.data, n, sdf.ctypes.data, w.ctypes.data, rgb.ctypes.data, found.ctypes.data)
+        assert released >= 0, "key list and table disagree"
+        return sdf, w, rgb, found.astype(bool), released
+
+    def upload_blocks(self, keys, sdf, w, rgb):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        sdf = np.ascontiguousarray(sdf, np.float32); w = np.ascontiguousarray(w, np.float32); rgb = np.ascontiguousarray(rgb, np.uint8)
+        self.L.emu_upload_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 3
+        rc = self.L.emu_upload_blocks(self.h, keys.ctypes.data, len(keys), sdf.ctypes.data, w.ctypes.data, rgb.ctypes.data)
+        assert rc == 0, f"map error flags 0x{rc:x}"
+
+    def rebuild_table(self):
+        self.L.emu_rebuild_table.argtypes = [C.c_void_p]
+        n = self.L.emu_rebuild_table(self.h)
+        assert n >= 0
+        return n
+
+    free_slots = property(lambda s: s.L.emu_free_slots(s.h))
 
     def full_map_mc(self):
         """vh_extract_mesh(VH_MESH_FULL_MAP): every allocated block meshed against the whole map; returns the triangle count"""

@@ -21,6 +21,9 @@
 #include <ucontext.h>
 
 #include <algorithm>
+#include <mutex>
+#include <string>
+#include <unordered_set>
 #include <vector>
 
 #define __device__

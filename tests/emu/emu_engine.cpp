@@ -7,6 +7,7 @@
 
 #include "../../voxel-hashing-sdf_b200/csrc/vh_alloc.cu"
 #include "../../voxel-hashing-sdf_b200/csrc/vh_mc.cu"
+#include "../../voxel-hashing-sdf_b200/csrc/vh_stream.cu"
 #include "../../voxel-hashing-sdf_b200/csrc/vh_params_host.h"
 
 namespace vh {
@@ -214,6 +215,78 @@ long long emu_full_map_mc(emu_engine* e) {
   e->full_valid = 1;
   return (e->engine_error & 1) ? -1 : t;
 }
+
+// ---- out-of-core tier (csrc/vh_stream.cu): the kernels, with the few host lines of vh_far_blocks / vh_evict_blocks / vh_upload_blocks restated
+struct FarArgs { StaticParams S; FrameParams F; DeviceView D; u64* out; int cap; int* count; };
+static void run_far(void* p) { FarArgs* a = static_cast<FarArgs*>(p); far_blocks_kernel(a->S, a->F, a->D, a->out, a->cap, a->count); }
+struct EvictArgs { DeviceView D; const u64* keys; int n; int* released; };
+static void run_evict(void* p) { EvictArgs* a = static_cast<EvictArgs*>(p); evict_kernel(a->D, a->keys, a->n, a->released); }
+struct UpArgs { DeviceView D; const u64* keys; int n; int* slots; const float* sdf; const float* wgt; const uint8_t* rgb; };
+static void run_up_insert(void* p) { UpArgs* a = static_cast<UpArgs*>(p); upload_insert_kernel(a->D, a->keys, a->n, a->slots); }
+static void run_up_scatter(void* p) { UpArgs* a = static_cast<UpArgs*>(p); upload_scatter_kernel(a->D, a->slots, a->n, a->sdf, a->wgt, a->rgb); }
+struct RebuildArgs { DeviceView D; uint32_t capacity; u64* k; int* s; uint32_t* st; int room; int* count; int n; };
+static void run_rebuild_collect(void* p) { RebuildArgs* a = static_cast<RebuildArgs*>(p); rebuild_collect_kernel(a->D, a->capacity, a->k, a->s, a->st, a->room, a->count); }
+static void run_rebuild_insert(void* p) { RebuildArgs* a = static_cast<RebuildArgs*>(p); rebuild_insert_kernel(a->D, a->k, a->s, a->st, a->n); }
+
+int emu_far_blocks(emu_engine* e, const float* c2w, int* out_xyz, int cap) {
+  FrameParams F; derive_frame_params(e->P, e->S, c2w, F); F.frame = 0;
+  std::vector<u64> out(std::max(cap, 1));
+  int count = 0;
+  FarArgs a{e->S, F, e->D, out.data(), out_xyz ? cap : 0, &count};
+  emu::run_grid(dim3((e->D.map.num_blocks + 255) / 256), dim3(256), run_far, &a);
+  const int m = std::min(count, out_xyz ? cap : 0);
+  std::sort(out.begin(), out.begin() + m);
+  for (int i = 0; i < m; i++) unpack_key(out[i], out_xyz[3 * i], out_xyz[3 * i + 1], out_xyz[3 * i + 2]);
+  return count;
+}
+
+int emu_rebuild_table(emu_engine* e) {
+  const uint32_t capacity = e->D.map.mask + 1;
+  const int room = (int)std::min<size_t>(capacity, 2 * (size_t)e->P.pool_blocks);
+  std::vector<u64> k(room); std::vector<int> s(room); std::vector<uint32_t> st(room);
+  int count = 0;
+  RebuildArgs a{e->D, capacity, k.data(), s.data(), st.data(), room, &count, 0};
+  emu::run_grid(dim3((capacity + 255) / 256), dim3(256), run_rebuild_collect, &a);
+  if (count > room) return -1;
+  std::fill(e->keys.begin(), e->keys.end(), KEY_EMPTY); std::fill(e->slots.begin(), e->slots.end(), -1); std::fill(e->stamps.begin(), e->stamps.end(), 0u);
+  a.n = count;
+  if (count > 0) emu::run_grid(dim3((count + 255) / 256), dim3(256), run_rebuild_insert, &a);
+  e->counters.visible_count = 0;
+  return count;
+}
+
+void emu_get_blocks(const emu_engine* e, const int* keys_xyz, int n, float* sdf, float* w, uint8_t* rgb, uint8_t* found, int* neg);
+// returns the number of blocks released; found[i] / planes as vh_download_blocks; the last frame's visible list is void afterwards
+int emu_evict_blocks(emu_engine* e, const int* keys_xyz, int n, float* sdf, float* w, uint8_t* rgb, uint8_t* found) {
+  std::vector<int> neg(std::max(n, 1));
+  emu_get_blocks(e, keys_xyz, n, sdf, w, rgb, found, neg.data());
+  std::vector<u64> packed(std::max(n, 1));
+  for (int i = 0; i < n; i++) packed[i] = pack_key(keys_xyz[3 * i], keys_xyz[3 * i + 1], keys_xyz[3 * i + 2]);
+  int released = 0;
+  EvictArgs a{e->D, packed.data(), n, &released};
+  emu::run_grid(dim3((n + 7) / 8), dim3(256), run_evict, &a);
+  if (released > 0) {      // key_heap: drop the released keys, keep the insertion order (host side, as vh_evict_blocks does)
+    const std::unordered_set<u64> gone(packed.begin(), packed.begin() + n);
+    int m = 0;
+    for (int i = 0; i < e->heap_counter; i++) if (!gone.count(e->key_heap[i])) e->key_heap[m++] = e->key_heap[i];
+    if (m != e->heap_counter - released) return -1;
+    e->heap_counter = m;
+  }
+  e->counters.visible_count = 0;
+  return released;
+}
+
+int emu_upload_blocks(emu_engine* e, const int* keys_xyz, int n, const float* sdf, const float* w, const uint8_t* rgb) {
+  std::vector<u64> packed(std::max(n, 1));
+  for (int i = 0; i < n; i++) packed[i] = pack_key(keys_xyz[3 * i], keys_xyz[3 * i + 1], keys_xyz[3 * i + 2]);
+  std::vector<int> slots(std::max(n, 1), -2);
+  UpArgs a{e->D, packed.data(), n, slots.data(), sdf, w, rgb};
+  emu::run_grid(dim3((n + 255) / 256), dim3(256), run_up_insert, &a);
+  emu::run_grid(dim3((n + 7) / 8), dim3(256), run_up_scatter, &a);
+  return e->map_error;
+}
+
+int emu_free_slots(const emu_engine* e) { return e->free_top; }
 
 // vh_shard_connect: every rank gets a view of every rank's table and planes (CUDA-IPC mappings on the GPU, pointers here)
 int emu_connect(emu_engine** ranks, int n) {

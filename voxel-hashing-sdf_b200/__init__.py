@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "vh_map_get_view",
     "vh_owner_of_block", "vh_shard_unique_id", "vh_shard_connect", "vh_integrate_sharded", "vh_shard_gather_mesh", "vh_shard_stats",
     "vh_mesh_order_merge",
+    "vh_far_blocks", "vh_blocks_resident", "vh_evict_blocks", "vh_upload_blocks",
 ]
 
 
@@ -110,6 +111,10 @@ def load_library():
     L.vh_visible_keys.argtypes = [vp, vp, ip, C.POINTER(ip)]
     L.vh_allocated_keys.argtypes = [vp, vp, ip, C.POINTER(ip)]
     L.vh_download_blocks.argtypes = [vp, vp, ip, vp, vp, vp, vp]
+    L.vh_far_blocks.argtypes = [vp, vp, vp, ip, vp]
+    L.vh_blocks_resident.argtypes = [vp, vp, vp, ip, vp]
+    L.vh_evict_blocks.argtypes = [vp, vp, ip, vp, vp, vp, vp]
+    L.vh_upload_blocks.argtypes = [vp, vp, ip, vp, vp, vp]
     L.vh_voxel_checksum.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.vh_extract_mesh.argtypes = [vp, ip, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.vh_save_ply.argtypes = [vp, C.c_char_p, ip]
@@ -148,6 +153,15 @@ def default_params(**kw) -> VhParams:
             raise AttributeError(f"vh_params has no field {k}")
         setattr(p, k, v)
     return p
+
+
+def blocks_resident(params, c2w, keys):
+    """reference residency rule (chunk cube + sphere around the frustum centre) for arbitrary block keys; host arithmetic only"""
+    keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+    c2w = np.ascontiguousarray(c2w, np.float32)
+    out = np.zeros(max(len(keys), 1), np.uint8)
+    _check(load_library().vh_blocks_resident(C.byref(params), _ptr(c2w), _ptr(keys), len(keys), _ptr(out)))
+    return out[:len(keys)].astype(bool)
 
 
 def owner_of_block(x: int, y: int, z: int, shard_count: int, shard_group: int = 8) -> int:
@@ -335,6 +349,34 @@ class TsdfEngine:
         found = np.zeros(n, np.uint8)
         _check(self.L.vh_download_blocks(self.h, _ptr(keys), n, _ptr(sdf), _ptr(w), _ptr(rgb), _ptr(found)))
         return sdf, w, rgb, found.astype(bool)
+
+    # -- out-of-core tier (between frames) ----------------------------------------------------------
+    def far_blocks(self, c2w):
+        """allocated blocks whose chunk fails the reference's residency rule for this pose (tsdf.cu:166-187,300-312)"""
+        c2w = np.ascontiguousarray(c2w, np.float32)
+        n = C.c_int(0)
+        _check(self.L.vh_far_blocks(self.h, _ptr(c2w), None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 3), np.int32)
+        _check(self.L.vh_far_blocks(self.h, _ptr(c2w), _ptr(out), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def evict_blocks(self, keys, want_rgb=True):
+        """download the blocks, then release them from the map: (sdf, weight, rgb, found)"""
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        n = len(keys)
+        sdf = np.zeros((n, 512), np.float32)
+        w = np.zeros((n, 512), np.float32)
+        rgb = np.zeros((n, 512, 3), np.uint8) if want_rgb else None
+        found = np.zeros(n, np.uint8)
+        _check(self.L.vh_evict_blocks(self.h, _ptr(keys), n, _ptr(sdf), _ptr(w), _ptr(rgb), _ptr(found)))
+        return sdf, w, rgb, found.astype(bool)
+
+    def upload_blocks(self, keys, sdf, weight, rgb=None):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        sdf = np.ascontiguousarray(sdf, np.float32); weight = np.ascontiguousarray(weight, np.float32)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        assert sdf.size == len(keys) * 512 and weight.size == len(keys) * 512 and (rgb is None or rgb.size == len(keys) * 512 * 3)
+        _check(self.L.vh_upload_blocks(self.h, _ptr(keys), len(keys), _ptr(sdf), _ptr(weight), _ptr(rgb)))
 
     def checksum(self):
         ss, sw, no, nn = C.c_double(), C.c_double(), C.c_uint64(), C.c_uint64()

@@ -112,6 +112,7 @@ static int reset_map(vh_engine* e) {
   init_free_list_kernel<<<(nb + 255) / 256, 256, 0, e->stream>>>(D.map.free_list, nb);
   CK(cudaMemcpyAsync(D.map.free_top, &nb, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  e->tombstones = 0;
   e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0; e->forced_syncs = 0; e->integrate_launches = 0;
   memset(e->h_block, 0, sizeof(*e->h_block));
   return VH_OK;

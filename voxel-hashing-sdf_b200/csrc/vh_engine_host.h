@@ -57,6 +57,7 @@ struct vh_engine {
   uint32_t integrate_launches = 0;      // since the last reset: bounds every voxel weight
   uint32_t weight_bound_bias = 0;       // env VH_INTEGRATE_EXACT_COLOR=1: pretend weights are large (forces the general colour path)
   int mc_parity = 0;                    // which McQueueCtl slot the next marching-cubes launch uses
+  uint32_t tombstones = 0;              // table entries released by vh_evict_blocks since the last rebuild (vh_stream.cu)
   // multi-GPU (vh_shard.cu)
   vh_shard_state* shard = nullptr;
   PeerTable* d_peers = nullptr;
