@@ -265,9 +265,9 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
                             f2 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[2], color);
             p0 = edge_finish(B, f0, color); p1 = edge_finish(B, f1, color); p2 = edge_finish(B, f2, color);
           } else {
-          p0 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[0], color);
-          p1 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[1], color);
-          p2 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[2], color);
+            p0 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[0], color);
+            p1 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[1], color);
+            p2 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[2], color);
           }
           valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
         }
