@@ -167,9 +167,16 @@ __device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int
 
 // Mesh one block with the whole warp: stage the 9^3 tile, pass 1 lists candidate triangles, pass 2 writes the survivors.
 // B.nb_slot[0..8) holds the pool slots of the block and its seven upper neighbours (-1 = absent), `present` the same as bits.
+// REV 1 keeps the cube index of every voxel that has triangles (one byte per voxel per warp) so that the emit pass does not
+// rebuild it from eight shared-memory reads per candidate triangle; REV 0 has no such array.
+template <int REV> struct CubeCache { __device__ static __forceinline__ unsigned char* get(int) { return nullptr; } };
+template <> struct CubeCache<1> {
+  __device__ static __forceinline__ unsigned char* get(int wid) { __shared__ unsigned char s_cube[MC_WARPS][BLOCK_VOX]; return s_cube[wid]; }
+};
+
 template <bool SHARDED, int REV>
 __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D, const int slot, const unsigned present, const int (&halo)[7],
-                                          float* tile, unsigned short* wlist, const signed char* s_tri, const unsigned char* s_ntri,
+                                          float* tile, unsigned short* wlist, unsigned char* cube_cache, const signed char* s_tri, const unsigned char* s_ntri,
                                           const bool color, unsigned long long* __restrict__ out_offset, int* __restrict__ out_count,
                                           const int lane, const uint32_t frame) {
     // okbits bit q: every corner block a voxel with boundary mask q touches is present
@@ -226,7 +233,11 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
       const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
       const int need = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);
       int nt = 0;
-      if ((okbits >> need) & 1u) nt = s_ntri[cube_index(tile, lx, ly, lz)];     // 0 for cube index 0 and 255
+      if ((okbits >> need) & 1u) {
+        const int ci = cube_index(tile, lx, ly, lz);
+        nt = s_ntri[ci];                                                         // 0 for cube index 0 and 255
+        if (REV == 1 && nt > 0) cube_cache[t] = (unsigned char)ci;
+      }
       if (!__any_sync(0xffffffffu, nt > 0)) continue;
       int incl = nt;
 #pragma unroll
@@ -259,7 +270,7 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
           const int item = wl[e];
           const int t = item >> 3, k = item & 7;
           const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
-          const signed char* row = s_tri + cube_index(tile, lx, ly, lz) * 16 + 3 * k;
+          const signed char* row = s_tri + (REV == 1 ? (int)cube_cache[t] : cube_index(tile, lx, ly, lz)) * 16 + 3 * k;
           if (REV == 1) {
             const EdgeFetch f0 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[0], color), f1 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[1], color),
                             f2 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[2], color);
@@ -422,7 +433,7 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
     __syncwarp();                              // previous block's readers of s_nb / tile / list are done
     if (lane < 8) { s_nb[wid][lane] = w->nb[lane]; s_nbo[wid][lane] = SHARDED ? (int)w->owner[lane] : 0; }
     __syncwarp();
-    my_tris += (unsigned long long)mesh_block<SHARDED, REV>(C, D, cur_slot, present, halo, tile, s_list[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
+    my_tris += (unsigned long long)mesh_block<SHARDED, REV>(C, D, cur_slot, present, halo, tile, s_list[wid], CubeCache<REV>::get(wid), s_tri, s_ntri, color, out_offset, out_count, lane, frame);
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
