@@ -227,13 +227,28 @@ __device__ __forceinline__ int merge_rank(const float* __restrict__ t, int n, fl
   }
   return lo;
 }
+// The same rank, found from where it is expected: the sequence is t0 plus j increments up to rounding, so (v - t0) / del
+// lands within an element of the boundary; a walk of at most three elements either way settles the exact place (the
+// answer is defined by the comparisons with the stored elements, never by the estimate), and anything else — a direction
+// component of zero (all elements +inf), non-finite values — falls back to the bisection above.
+__device__ __forceinline__ int merge_rank_near(const float* __restrict__ t, int n, float v, bool ties_first, float inv_del) {
+  const float p = __fmul_rn(__fsub_rn(v, t[0]), inv_del);
+  int j = p >= 0.0f ? (p < (float)n ? (int)p + 1 : n) : 0;               // NaN -> 0
+#pragma unroll 1
+  for (int tries = 0; tries < 4; tries++) {
+    if (j > 0) { const float x = t[j - 1]; if (!(x < v || (ties_first && x == v))) { j--; continue; } }
+    if (j < n) { const float x = t[j]; if (x < v || (ties_first && x == v)) { j++; continue; } }
+    return j;
+  }
+  return merge_rank(t, n, v, ties_first);
+}
 
 // phases 0-2 for the CTA's tile of rays: skeys[step * RAYS + ray] = block visited at that step (KEY_EMPTY where the block is
 // outside the key range), s_death[ray] = last step the ray takes (K if it never reaches a bound). All threads of the CTA.
 __device__ __forceinline__ void merge_fill_keys(const StaticParams& S, const FrameParams& F, const float* __restrict__ depth, int tile_x, int tile_y,
                                                 u64* __restrict__ skeys, float* __restrict__ sT, int* __restrict__ s_death) {
   __shared__ int s_cur[RAYS][3], s_step[RAYS][3], s_last[RAYS][3], s_alive[RAYS];
-  __shared__ float s_del[RAYS][3];
+  __shared__ float s_del[RAYS][3], s_inv[RAYS][3];
   const int K = S.max_steps;
   const int tid = threadIdx.x;
 
@@ -251,6 +266,7 @@ __device__ __forceinline__ void merge_fill_keys(const StaticParams& S, const Fra
       s_last[tid][a] = (R.istep[a] != 0 && ahead >= 1 && ahead <= (long long)K) ? (int)ahead - 1 : -1;
       sT[(tid * 3 + a) * K] = R.tmax[a];
       s_del[tid][a] = R.tdel[a];
+      s_inv[tid][a] = R.tdel[a] > 0.0f ? fdiv(1.0f, R.tdel[a]) : 0.0f;         // estimate only (merge_rank_near); +inf -> 0
     }
   }
   for (int i = tid; i < K * RAYS; i += (int)blockDim.x) skeys[i] = KEY_EMPTY;
@@ -265,21 +281,31 @@ __device__ __forceinline__ void merge_fill_keys(const StaticParams& S, const Fra
   }
   __syncthreads();
 
-  // phase 2: every element finds its step and the block the ray is in when it takes it
-  for (int e = tid; e < RAYS * 3 * K; e += (int)blockDim.x) {
-    const int ra = e / K, k = e - ra * K, ray = ra / 3, a = ra - ray * 3;
+  // phase 2: every element finds its step and the block the ray is in when it takes it. A warp takes (ray, axis) pairs,
+  // its lanes the elements k of the pair; an element whose step is already beyond the cap after the first count is dropped.
+  const int nwarps = (int)blockDim.x >> 5, wid = tid >> 5, lane = tid & 31;
+  for (int ra = wid; ra < RAYS * 3; ra += nwarps) {
+    const int ray = ra / 3, a = ra - ray * 3;
     if (!s_alive[ray]) continue;
     const int b = a == 0 ? 1 : 0, c = a == 2 ? 1 : 2;                 // the other two axes
-    const float v = sT[e];
     const int pa = axis_priority(a);
-    const int nb = merge_rank(sT + (size_t)(ray * 3 + b) * K, K, v, axis_priority(b) < pa);
-    const int nc = merge_rank(sT + (size_t)(ray * 3 + c) * K, K, v, axis_priority(c) < pa);
-    const int pos = k + nb + nc;
-    if (pos < 0 || pos >= K) continue;
-    int cur[3];
-    cur[a] = s_cur[ray][a] + k * s_step[ray][a]; cur[b] = s_cur[ray][b] + nb * s_step[ray][b]; cur[c] = s_cur[ray][c] + nc * s_step[ray][c];
-    if (key_in_range(cur[0], cur[1], cur[2])) skeys[pos * RAYS + ray] = pack_key(cur[0], cur[1], cur[2]);
-    if (k == s_last[ray][a]) atomicMin(&s_death[ray], pos);           // this step moves the ray onto its bound (tsdf.cu:2219,2224,2229)
+    const bool tb = axis_priority(b) < pa, tc = axis_priority(c) < pa;
+    const float* Ta = sT + (size_t)ra * K;
+    const float* Tb = sT + (size_t)(ray * 3 + b) * K;
+    const float* Tc = sT + (size_t)(ray * 3 + c) * K;
+    const float ib = s_inv[ray][b], ic = s_inv[ray][c];
+    for (int k = lane; k < K; k += 32) {
+      const float v = Ta[k];
+      const int nb = merge_rank_near(Tb, K, v, tb, ib);
+      if (k + nb >= K) continue;
+      const int nc = merge_rank_near(Tc, K, v, tc, ic);
+      const int pos = k + nb + nc;
+      if (pos < 0 || pos >= K) continue;
+      int cur[3];
+      cur[a] = s_cur[ray][a] + k * s_step[ray][a]; cur[b] = s_cur[ray][b] + nb * s_step[ray][b]; cur[c] = s_cur[ray][c] + nc * s_step[ray][c];
+      if (key_in_range(cur[0], cur[1], cur[2])) skeys[pos * RAYS + ray] = pack_key(cur[0], cur[1], cur[2]);
+      if (k == s_last[ray][a]) atomicMin(&s_death[ray], pos);         // this step moves the ray onto its bound (tsdf.cu:2219,2224,2229)
+    }
   }
   __syncthreads();
 }
