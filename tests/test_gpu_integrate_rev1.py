@@ -16,7 +16,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("VH_TEST_REV1") != "1", reason="opt-in kernel revision: set VH_TEST_REV1=1 (tools/gpu_rev1.sh)")]
 
 
-@pytest.fixture(params=["4", "3"], ids=["4ctas", "3ctas"])
+@pytest.fixture(params=["4", "3", "7"], ids=["4ctas", "3ctas", "7x128"])
 def rev1(request, monkeypatch):
     monkeypatch.setenv("VH_INTEGRATE_REV", "1")
     monkeypatch.setenv("VH_INTEGRATE_CTAS", request.param)

@@ -142,7 +142,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   StaticParams& S = e->S;
   derive_static_params(*p, S);
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
-  { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '2' && v[0] <= '4') ? v[0] - '0' : 4; }   // tuning knobs
+  { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && ((v[0] >= '2' && v[0] <= '4') || v[0] == '7')) ? v[0] - '0' : 4; }   // tuning knobs (7: revision 1 only, 7 CTAs of 128 threads)
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
