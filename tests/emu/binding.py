@@ -9,7 +9,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "libvh_emu.so")
+LIB_NAME = os.environ.get("VH_EMU_LIB", "libvh_emu.so")      # libvh_emu_asan.so: the AddressSanitizer build (tests/emu/Makefile)
+LIB = os.path.join(HERE, LIB_NAME)
 
 
 class IntegrateIO(C.Structure):
@@ -32,7 +33,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["make", "-s", "-B", "-C", HERE, "libvh_emu.so"])   # always rebuilt: it mirrors the kernel sources of the moment
+        subprocess.check_call(["make", "-s", "-B", "-C", HERE, LIB_NAME])   # always rebuilt: it mirrors the kernel sources of the moment
         _lib = C.CDLL(LIB)
         _lib.emu_integrate.argtypes = [C.POINTER(IntegrateIO)]
         _lib.emu_integrate.restype = C.c_int

@@ -66,6 +66,11 @@ typedef void* cudaEvent_t;
 typedef int cudaError_t;
 
 // ---- fibres ---------------------------------------------------------------------------------------------------------
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>      // fibre switches must be announced to AddressSanitizer (make -C tests/emu asan)
+#define EMU_ASAN 1
+#endif
+
 namespace emu {
 
 struct Group { int size = 0, arrived = 0; unsigned gen = 0; unsigned long long slot[2][32]; unsigned parity = 0; };
@@ -75,6 +80,7 @@ struct Fibre {
   uint3 tid;
   bool done = false;
   unsigned warp_parity = 0;   // which exchange buffer this lane uses for its next warp collective
+  void* asan_fake = nullptr;  // AddressSanitizer's fake-stack handle while the fibre is switched out
 };
 struct Cta {
   std::vector<Fibre> fibres;
@@ -87,12 +93,23 @@ struct Cta {
   void (*entry)(void*) = nullptr;
   void* arg = nullptr;
   char* dyn_smem = nullptr;      // dynamic shared memory of the CTA (third launch parameter)
+  const void* sched_stack = nullptr; size_t sched_stack_size = 0;     // the scheduler's (OS thread's) stack, for AddressSanitizer
+  size_t fibre_stack_bytes = 0;
 };
 extern Cta* g_cta;
 extern unsigned long long g_collectives, g_events;
 extern unsigned g_rcp_seed;
 
-inline void yield() { swapcontext(&g_cta->cur->ctx, &g_cta->sched); }
+inline void yield() {
+#ifdef EMU_ASAN
+  Fibre* f = g_cta->cur;
+  __sanitizer_start_switch_fiber(&f->asan_fake, g_cta->sched_stack, g_cta->sched_stack_size);
+  swapcontext(&f->ctx, &g_cta->sched);
+  __sanitizer_finish_switch_fiber(f->asan_fake, nullptr, nullptr);
+#else
+  swapcontext(&g_cta->cur->ctx, &g_cta->sched);
+#endif
+}
 inline void barrier(Group& g) {
   const unsigned my = g.gen;
   if (++g.arrived == g.size) { g.arrived = 0; g.gen++; g_events++; } else while (g.gen == my) yield();

@@ -11,8 +11,14 @@ unsigned g_rcp_seed = 12345u;
 
 void trampoline() {
   Cta* c = g_cta;
+#ifdef EMU_ASAN
+  __sanitizer_finish_switch_fiber(nullptr, &c->sched_stack, &c->sched_stack_size);      // first entry: learn the scheduler's stack
+#endif
   c->entry(c->arg);
   c->cur->done = true;
+#ifdef EMU_ASAN
+  __sanitizer_start_switch_fiber(nullptr, c->sched_stack, c->sched_stack_size);         // nullptr: this fibre never resumes
+#endif
   swapcontext(&c->cur->ctx, &c->sched);
 }
 
@@ -47,7 +53,14 @@ void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg, size_t dyn
         Fibre& f = cta.fibres[t];
         if (f.done) continue;
         cta.cur = &f;
+#ifdef EMU_ASAN
+        void* fake = nullptr;
+        __sanitizer_start_switch_fiber(&fake, f.stack, stack_bytes);
         swapcontext(&cta.sched, &f.ctx);
+        __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#else
+        swapcontext(&cta.sched, &f.ctx);
+#endif
         if (f.done) { live--; g_events++; }
       }
       if (g_events == events_before) {   // a whole round in which no barrier opened and no thread finished
