@@ -8,6 +8,8 @@ namespace emu {
 Cta* g_cta = nullptr;
 unsigned long long g_collectives = 0, g_events = 0;
 unsigned g_rcp_seed = 12345u;
+int g_order_mode = -1;
+unsigned g_order_seed = 1u;
 
 void trampoline() {
   Cta* c = g_cta;
@@ -33,6 +35,13 @@ void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg, size_t dyn
   cta.dyn_smem = dyn.data() + (16 - (reinterpret_cast<uintptr_t>(dyn.data()) & 15)) % 16;
   Cta* const outer = g_cta;
   g_cta = &cta;
+  if (g_order_mode < 0) {
+    const char* v = getenv("VH_EMU_ORDER");
+    g_order_mode = !v ? 0 : (!strncmp(v, "reverse", 7) ? 1 : (!strncmp(v, "random", 6) ? 2 : 0));
+    if (g_order_mode == 2 && strchr(v, ':')) g_order_seed = (unsigned)atoi(strchr(v, ':') + 1) * 2654435761u + 1u;
+  }
+  std::vector<int> order(nthreads);
+  for (int t = 0; t < nthreads; t++) order[t] = t;
   for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
     cta.bid = uint3{bx, by, bz};
     cta.warps.assign((nthreads + 31) / 32, Group());
@@ -49,7 +58,13 @@ void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg, size_t dyn
     int live = nthreads;
     while (live > 0) {
       const unsigned long long events_before = g_events;
-      for (int t = 0; t < nthreads; t++) {
+      // Scheduling order of a round. The default runs the threads in index order, which can hide a missing barrier (the
+      // writer happens to run before the reader). VH_EMU_ORDER=reverse or =random:<seed> runs every round in another order:
+      // results that depend on the order point at unsynchronised communication through shared or global memory.
+      if (g_order_mode == 1) { for (int t = 0; t < nthreads; t++) order[t] = nthreads - 1 - t; }
+      else if (g_order_mode == 2) { for (int t = nthreads - 1; t > 0; t--) { g_order_seed = g_order_seed * 1664525u + 1013904223u; std::swap(order[t], order[(g_order_seed >> 8) % (unsigned)(t + 1)]); } }
+      for (int oi = 0; oi < nthreads; oi++) {
+        const int t = order[oi];
         Fibre& f = cta.fibres[t];
         if (f.done) continue;
         cta.cur = &f;

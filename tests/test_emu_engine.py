@@ -287,3 +287,20 @@ def test_emulated_full_map_extraction(vh, ob, synth, mc_rev):
         full_xyz, full_rgb = e.block_triangles(keys, full_map=True)
         assert full_xyz.shape == full_xyz_o.shape and np.array_equal(full_xyz.view(np.uint32), full_xyz_o.view(np.uint32)) and np.array_equal(full_rgb, full_rgb_o)
         assert n_full > len(ref_xyz) > 0
+
+
+def test_emulated_engine_under_another_thread_order():
+    """the emulator runs a CTA's threads round-robin in index order, which could hide a missing barrier (the writer happens to
+    run first); VH_EMU_ORDER re-runs with every round in reverse / random order — results must not depend on it"""
+    import os
+    import subprocess
+    import sys
+    from emu.binding import lib
+    lib()                                     # built once, here; the child processes load it as it is
+    here = os.path.dirname(os.path.abspath(__file__))
+    for order in ("reverse", "random:3"):
+        env = dict(os.environ, VH_EMU_ORDER=order, VH_EMU_NO_REBUILD="1")
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_engine.py"), "-x", "-q", "-p", "no:cacheprovider",
+                            "-k", "matches_oracle and 1-1-1 or sharded and 3 or merge_equals"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+        assert r.returncode == 0, f"VH_EMU_ORDER={order}:\n{r.stdout[-2000:]}"
+        assert "3 passed" in r.stdout, r.stdout[-500:]
