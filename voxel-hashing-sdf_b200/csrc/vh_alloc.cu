@@ -213,7 +213,8 @@ alloc_visible_kernel(const StaticParams S, const FrameParams F, const float* __r
 // sequential march (~40 dependent instructions per step, 100 steps, ~20 us) becomes ~2 us of parallel work, and all of
 // the CTA's keys are classified and inserted in rounds of 256 instead of 200 behind a marching warp.
 // Non-finite crossing times (a pose with NaNs) cannot index out of range: positions are checked, unwritten steps stay empty.
-constexpr int ALLOC1_MAX_SMEM = 200 * 1024;
+// Shared memory: 160 B per step of the cap (16 KB at the reference's 100 steps; 172 KB at the 1,100 of the room-scale config).
+constexpr int ALLOC1_MAX_SMEM = 224 * 1024;      // of the 227 KB a CTA can have: step caps up to ~1,400
 
 __device__ __forceinline__ int axis_priority(int a) { return a == 1 ? 0 : (a == 2 ? 1 : 2); }   // ties: y, then z, then x
 
@@ -320,7 +321,7 @@ alloc_visible_kernel_r1(const StaticParams S, const FrameParams F, const float* 
   const int K = S.max_steps;
   u64* skeys = dyn;                                                   // [K][RAYS]
   float* sT = reinterpret_cast<float*>(dyn + (size_t)K * RAYS);       // [RAYS][3][K] crossing times
-  int* s_first = reinterpret_cast<int*>(sT + (size_t)RAYS * 3 * K);   // [K * RAYS] entries first seen this frame
+  int* s_first = reinterpret_cast<int*>(sT);                          // [K * RAYS] entries first seen this frame: reuses the crossing times, dead after phase 2
   __shared__ int s_death[RAYS];
   __shared__ int s_cnt, s_base;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -373,7 +374,7 @@ alloc_visible_kernel_r1(const StaticParams S, const FrameParams F, const float* 
 }
 
 inline size_t alloc_r1_smem_bytes(int max_steps) {
-  return (size_t)max_steps * RAYS * sizeof(u64) + (size_t)RAYS * 3 * max_steps * sizeof(float) + (size_t)max_steps * RAYS * sizeof(int);
+  return (size_t)max_steps * RAYS * sizeof(u64) + (size_t)RAYS * 3 * max_steps * sizeof(float);     // keys + crossing times (160 B per step)
 }
 
 #ifndef VH_HOST_EMU
