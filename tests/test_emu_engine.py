@@ -98,7 +98,7 @@ def test_emulated_sharded_map_equals_single_map(vh, ob, synth, nranks, group):
         return engine_params(vh, sc, CASE, num_buckets=1 << 12, pool_blocks=1 << 12, tri_arena_bytes=8 << 20, shard_rank=rank, shard_count=n,
                              shard_group=group)
 
-    with EmuGroup(make, nranks, mc_rev=nranks - 2) as g:      # 3 ranks: with the mesh kernel's emit-pass revision
+    with EmuGroup(make, nranks, mc_rev=nranks - 2, alloc_rev=nranks - 2) as g:      # 3 ranks: with the allocation and marching-cubes revisions
         for i in range(3):
             d, rgb, c2w = sc.frame(i)
             o.process_frame(d, rgb, c2w)

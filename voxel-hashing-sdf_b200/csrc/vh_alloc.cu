@@ -339,9 +339,10 @@ alloc_visible_kernel_r1(const StaticParams S, const FrameParams F, const float* 
     if (key != KEY_EMPTY) {
       int bx, by, bz;
       unpack_key(key, bx, by, bz);
-      bool ok = chunk_is_candidate(S, F, block_to_chunk(bx, bpc), block_to_chunk(by, bpc), block_to_chunk(bz, bpc));   // tsdf.cu:2164
+      // sharded map: the (cheap) ownership test first, so that a rank spends the two geometric tests on its own blocks only
+      bool ok = S.shard_count <= 1 || owner_of_block(bx, by, bz, S.shard_count, S.shard_group) == S.shard_rank;
+      if (ok) ok = chunk_is_candidate(S, F, block_to_chunk(bx, bpc), block_to_chunk(by, bpc), block_to_chunk(bz, bpc));   // tsdf.cu:2164
       if (ok) ok = block_in_frustum(S, F, bx, by, bz);                                                                  // tsdf.cu:2165
-      if (ok && S.shard_count > 1) ok = owner_of_block(bx, by, bz, S.shard_count, S.shard_group) == S.shard_rank;
       if (!ok) key = KEY_EMPTY;
     }
     if (__ballot_sync(0xffffffffu, key != KEY_EMPTY) != 0) {
