@@ -57,7 +57,13 @@ def parse():
     ap.add_argument("--no-mc", action="store_true", help="integration only (F_int); default runs working-set MC every frame like the reference")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ray-steps", type=int, default=0, help="max_ray_steps; 0 = the reference's 100 (configs 3/4: ~1100 reach the walls, SURVEY.md section 8d)")
+    ap.add_argument("--pool-blocks", type=int, default=0, help="voxel-block pool size; 0 = 3 Mi blocks (a long-ray config 4 run needs ~8 Mi)")
     return ap.parse_args()
+
+
+def ray_kw(args):
+    return dict(max_ray_steps=args.ray_steps) if args.ray_steps else {}
 
 
 def workload(args, rank):
@@ -72,6 +78,7 @@ def config_dict(args, cfg, sc, world):
     return {
         "workload": f"BASELINE config {args.config[1]}: synthetic {sc.width}x{sc.height} depth+rgb sequence, {sc.n_frames} frames, "
                     f"{cfg['vox_size'] * 1000:g} mm voxels, 8^3 blocks, {cfg['num_buckets']}-bucket x4 hash, trunc {cfg['trunc'] * 100:g} cm, MaxDepth {cfg['max_depth']:g}",
+        "max_ray_steps": args.ray_steps or 100,
         "frames_per_step": FRAMES_PER_STEP,
         "per_frame_path": "upload + allocate + integrate" + ("" if args.no_mc else " + working-set marching cubes"),
         "color": not args.no_color,
@@ -88,7 +95,7 @@ def cpu_reference_run(args, frames_wanted, per_step_frames, steps, warmup):
     from oracle import binding as ob
     synth, cfg, sc = workload(args, 0)
     p = ob.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"], voxels_per_block=8,
-                            use_color=0 if args.no_color else 1, run_mc=0 if args.no_mc else 1, num_threads=0)
+                            use_color=0 if args.no_color else 1, run_mc=0 if args.no_mc else 1, num_threads=0, **ray_kw(args))
     o = ob.Oracle(p)
     threads = ob.lib().vo_threads()
     frames = [sc.frame(i) for i in range(frames_wanted)]
@@ -201,8 +208,8 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"],
-                            num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=3 << 20,
-                            use_color=1 if color else 0, mc_per_frame=0 if args.no_mc else 1, device=local, tri_arena_bytes=4 << 30)
+                            num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=args.pool_blocks or (3 << 20),
+                            use_color=1 if color else 0, mc_per_frame=0 if args.no_mc else 1, device=local, tri_arena_bytes=4 << 30, **ray_kw(args))
     eng = vh.TsdfEngine(p)
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
     dptr = lambda t, i: t[i].data_ptr()
@@ -443,9 +450,9 @@ def run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, po
     out = {}
     for label, mc in (("integrate_only", 0), ("with_marching_cubes", 1)):
         p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"],
-                                num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=(3 << 20) // world + (1 << 18),
+                                num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=(args.pool_blocks or (3 << 20)) // world + (1 << 18),
                                 use_color=1 if color else 0, mc_per_frame=mc, device=local, shard_rank=rank, shard_count=world,
-                                tri_arena_bytes=(4 << 30) // world + (1 << 30))
+                                tri_arena_bytes=(4 << 30) // world + (1 << 30), **ray_kw(args))
         eng = vh.TsdfEngine(p)
         ids = [vh.TsdfEngine.shard_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
