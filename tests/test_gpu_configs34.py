@@ -2,7 +2,7 @@
 Config 3: 1280x720, 4 mm voxels, 2^24-bucket hash, truncation 3 cm, full-map mesh extraction.
 Config 4: 10 m room centred on the origin (negative block coordinates), 2 mm voxels, truncation 1 cm.
 Written after the round's GPU time had run out (the same shapes pass under the CPU emulation of the kernel sources,
-tools/emu_headline_check.py); gated behind VH_TEST_REV1=1 until they have run once on a B200 (tools/gpu_rev1.sh)."""
+tests/emu/headline_check.py); gated behind VH_TEST_REV1=1 until they have run once on a B200 (tools/gpu_rev1.sh)."""
 import os
 
 import numpy as np
