@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """CPU baseline: the oracle (port of the reference's algorithm) on the box's host cores, per stage, with 1
-thread and with all OpenMP threads. usage: python tools/bench_cpu_oracle.py --config C1 --frames 6"""
+thread and with all OpenMP threads. usage: python oracle/tools/bench_cpu_oracle.py --config C1 --frames 6"""
 import argparse, importlib, json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from oracle import binding as ob  # noqa: E402
 
 ap = argparse.ArgumentParser(); ap.add_argument("--config", default="C1"); ap.add_argument("--frames", type=int, default=6); a = ap.parse_args()

@@ -2,8 +2,8 @@
 """Baseline: the reference's OWN CUDA build (its src/tsdf.cu compiled for sm_100a by oracle/build_ref_cuda.sh) against this
 engine on the same B200, same synthetic frames, same parameters. Run on the GPU box:
 
-    python tools/bench_ref_cuda.py --config R8 --frames 12          # reference-sized blocks (18 cm) at 8^3 voxels
-    python tools/bench_ref_cuda.py --config C1 --frames 4           # BASELINE config 1 (1 cm voxels), enlarged tables
+    python oracle/tools/bench_ref_cuda.py --config R8 --frames 12          # reference-sized blocks (18 cm) at 8^3 voxels
+    python oracle/tools/bench_ref_cuda.py --config C1 --frames 4           # BASELINE config 1 (1 cm voxels), enlarged tables
 
 Prints one JSON line. The reference call is GpuTsdfGenerator::processFrame, fully synchronous, timed with a wall clock
 per call; ours is vh_integrate (same contract) timed the same way. BASELINE config 2 (5 mm) is not
@@ -18,7 +18,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
