@@ -2,7 +2,8 @@
 """Static instruction count of the integrate kernels' step loop on its hot path (rare blocks — out-of-line calls, the
 negative-voxel recount — are skipped), from the SASS of the built object. No GPU needed.
 usage: tools/sass_hot_path.py <substring of the mangled kernel name> [full]   e.g. integrate_kernel_r1ILb1ELb0ELb1ELb1ELi4"""
-import re, subprocess, sys
+import re, signal, subprocess, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # `| head` closes the pipe early
 import os
 obj = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "voxel-hashing-sdf_b200", "build", "vh_integrate.o")
 syms = sorted(set(re.findall(r"_ZN2vh[0-9A-Za-z_]*", subprocess.run(["cuobjdump", "-elf", obj], capture_output=True, text=True).stdout)))
