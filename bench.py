@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ray-steps", type=int, default=0, help="max_ray_steps; 0 = the reference's 100 (configs 3/4: ~1100 reach the walls, SURVEY.md section 8d)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames in one step; 0 = 50 (config 4 with long rays allocates ~0.9 M blocks per frame: use 4)")
     ap.add_argument("--pool-blocks", type=int, default=0, help="voxel-block pool size; 0 = 3 Mi blocks (a long-ray config 4 run needs ~8 Mi)")
     return ap.parse_args()
 
@@ -326,11 +327,13 @@ def run_ours(args):
     # ---- per-kernel profile pass (untimed for the headline): CUDA-event time of every stage of every frame ----
     eng.reset()
     acc = dict(alloc=0.0, integrate=0.0, mc=0.0, upload=0.0, updates=0, visible=0, tris=0, culled=0)
+    per_frame_rows = []          # (frame, ms_integrate, voxel updates, visible blocks, blocks discarded whole)
     for i in frames_of(n_timed):
         eng.integrate_device(dptr(d_depth, i), rgb_dev(i), poses[i])
         s = eng.stats()
         acc["alloc"] += s.ms_alloc; acc["integrate"] += s.ms_integrate; acc["mc"] += s.ms_mc
         acc["updates"] += s.voxel_updates; acc["visible"] += s.visible_blocks; acc["tris"] += s.triangles; acc["culled"] += s.culled_blocks
+        per_frame_rows.append((i, s.ms_integrate, s.voxel_updates, s.visible_blocks, s.culled_blocks, s.ms_alloc, s.ms_mc, s.triangles))
     clocks = sampler.stop() if sampler else None
     st_last = eng.stats()
     allocated = st_last.allocated_blocks
@@ -377,6 +380,17 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     ach = bytes_int / (ms_int * 1e-3) / 1e9 if ms_int > 0 else 0.0
+    # the same fraction frame by frame (the mix matters: frames in which few voxels pass the gate carry few algorithmic bytes)
+    def frame_bytes(u, v):
+        return 16.0 * u + 4.0 * W * H + 12.0 * v + ((8.0 * u + 3.0 * W * H) if color else 0.0)
+    fr = sorted(frame_bytes(r[2], r[3]) / (r[1] * 1e-3) / 1e9 / peak for r in per_frame_rows if r[1] > 0)
+    frac_frames = {"min": fr[0], "p10": fr[len(fr) // 10], "median": fr[len(fr) // 2], "p90": fr[(9 * len(fr)) // 10], "max": fr[-1]} if fr else None
+    dump = os.environ.get("VH_BENCH_DUMP")
+    if dump and rank == 0:
+        with open(dump, "w") as f:
+            f.write("frame,ms_integrate,voxel_updates,visible_blocks,blocks_discarded,ms_alloc,ms_mc,triangles\n")
+            for r in per_frame_rows:
+                f.write(",".join(str(x) for x in r) + "\n")
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "integrate_traffic.json")
     if os.path.exists(tpath) and args.config == "C2" and color:
@@ -402,7 +416,7 @@ def run_ours(args):
                       "arena_compactions_in_500_frames": int(st_last.arena_compactions)},
         "roofline": {"kernel": "vh::integrate_kernel_r1" if os.environ.get("VH_INTEGRATE_REV") == "1" else "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int},
+                     "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int, "frac_per_frame": frac_frames},
         "roofline_mc": {"kernel": "vh::mc_filter_kernel + vh::mc_mesh_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
                         "peak": peak, "unit": "GB/s", "algorithmic_bytes_per_launch": bytes_mc, "avg_launch_ms": ms_mc},
         "clocks": clocks,
@@ -496,6 +510,8 @@ def run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, po
 
 if __name__ == "__main__":
     a = parse()
+    if a.frames_per_step > 0:
+        FRAMES_PER_STEP = a.frames_per_step
     if a.impl == "reference":
         run_reference_arm(a)
     else:

@@ -20,6 +20,8 @@ typedef unsigned long long u64;
 
 constexpr u64 KEY_EMPTY = ~0ull;
 constexpr u64 KEY_TOMB = ~0ull - 1;     // erased entry (vh_map_erase only; the TSDF engine never erases)
+constexpr int SLOT_UNSET = -1;          // entry claimed, slot not yet published
+constexpr int SLOT_POOL_FULL = -2;      // entry claimed while the pool was exhausted: the block has no storage
 constexpr int COORD_BIAS = 1 << 20;     // coordinates live in [-2^20, 2^20)
 
 enum MapError { MAP_OK = 0, MAP_TABLE_FULL = 1, MAP_POOL_FULL = 2, MAP_KEY_RANGE = 4 };
@@ -100,6 +102,10 @@ __device__ __forceinline__ int map_claim(const MapView& m, u64 key, bool& claime
 
 // Warp-aggregated pool allocation + key_heap append for the lanes that just claimed an entry.
 // Must be called by all lanes named in `active` (converged). One atomicSub and one atomicAdd per warp.
+// Pool exhausted: the lanes that got no slot publish SLOT_POOL_FULL (what vhashing.h's wait_slot expects; -1 means "claimed,
+// not yet published" and would make a reader spin), their share of the pop is handed back so that free_top never stays
+// negative (a later push — erase, evict — must land inside the stack; the reference clamps with atomicMax(link_head, -1),
+// blockalloc.h:62-86), and heap_counter advances only by the slots actually granted, so key_heap has no holes.
 __device__ __forceinline__ void map_assign_slots(const MapView& m, unsigned active, bool claimed, int entry, u64 key) {
   const unsigned newmask = __ballot_sync(active, claimed);
   if (newmask == 0) return;
@@ -109,7 +115,9 @@ __device__ __forceinline__ void map_assign_slots(const MapView& m, unsigned acti
   int top = 0, heap_base = 0;
   if (lane == leader) {
     top = atomicSub(m.free_top, n);
-    heap_base = atomicAdd(m.heap_counter, n);
+    const int granted = top >= n ? n : (top > 0 ? top : 0);
+    if (granted < n) atomicAdd(m.free_top, n - granted);
+    if (granted > 0) heap_base = atomicAdd(m.heap_counter, granted);
   }
   top = __shfl_sync(active, top, leader);
   heap_base = __shfl_sync(active, heap_base, leader);
@@ -120,10 +128,17 @@ __device__ __forceinline__ void map_assign_slots(const MapView& m, unsigned acti
       m.slots[entry] = m.free_list[idx];
       if (heap_base + rank < m.num_blocks) m.key_heap[heap_base + rank] = key;
     } else {
-      m.slots[entry] = -1;
+      m.slots[entry] = SLOT_POOL_FULL;
       atomicOr(m.error_flag, MAP_POOL_FULL);
     }
   }
+}
+
+// push a slot back on the free-list stack (erase / evict). A position outside the stack can only come from a pop that is
+// handing back its share at this very moment (see map_assign_slots): the slot is dropped rather than written out of bounds.
+__device__ __forceinline__ void map_release_slot(const MapView& m, int slot) {
+  const int pos = atomicAdd(m.free_top, 1);
+  if (pos >= 0 && pos < m.num_blocks) m.free_list[pos] = slot; else atomicOr(m.error_flag, MAP_POOL_FULL);
 }
 #endif  // __CUDACC__
 

@@ -166,14 +166,14 @@ struct HashTableBase {
     const int s = wait_slot(e);
     if (atomicCAS(&view.keys[e], p, vh::KEY_TOMB) != p) return 0;
     view.slots[e] = -1;
-    if (s >= 0) { const int pos = atomicAdd(view.free_top, 1); view.free_list[pos] = s; }
+    if (s >= 0) vh::map_release_slot(view, s);
     return 1;
   }
 
  private:
   __device__ int wait_slot(int e) const {
     int s;
-    while ((s = *reinterpret_cast<volatile int*>(&view.slots[e])) == -1) {}   // claimed, slot not yet published
+    while ((s = *reinterpret_cast<volatile int*>(&view.slots[e])) == vh::SLOT_UNSET) {}   // claimed, slot not yet published
     return s;                                                                 // >= 0, or -2 = pool was exhausted
   }
   __device__ int insert_slot(const Key& k, const Value* v, int* entry_out = nullptr) {
@@ -184,7 +184,7 @@ struct HashTableBase {
     if (e < 0) return -1;
     if (entry_out) *entry_out = e;
     if (!claimed) return wait_slot(e);
-    int slot = -2;
+    int slot = vh::SLOT_POOL_FULL;
     const int top = atomicSub(view.free_top, 1);
     if (top > 0) {
       slot = view.free_list[top - 1];

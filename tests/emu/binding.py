@@ -189,12 +189,14 @@ class EmuEngine:
         assert released >= 0, "key list and table disagree"
         return sdf, w, rgb, found.astype(bool), released
 
-    def upload_blocks(self, keys, sdf, w, rgb):
+    def upload_blocks(self, keys, sdf, w, rgb, check=True):
         keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
         sdf = np.ascontiguousarray(sdf, np.float32); w = np.ascontiguousarray(w, np.float32); rgb = np.ascontiguousarray(rgb, np.uint8)
         self.L.emu_upload_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 3
         rc = self.L.emu_upload_blocks(self.h, keys.ctypes.data, len(keys), sdf.ctypes.data, w.ctypes.data, rgb.ctypes.data)
-        assert rc == 0, f"map error flags 0x{rc:x}"
+        if check:
+            assert rc == 0, f"map error flags 0x{rc:x}"
+        return rc
 
     def rebuild_table(self):
         self.L.emu_rebuild_table.argtypes = [C.c_void_p]

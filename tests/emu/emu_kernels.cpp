@@ -22,6 +22,12 @@ void run_r1(void* p) {
   vh::integrate_kernel_r1<C, V, DL, CULL, 4>(a->S, a->F, a->px, a->D);
 }
 
+template <bool C, bool V, bool DL, bool CULL, int NS>
+void run_r2(void* p) {
+  IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
+  vh::integrate_kernel_r2<C, V, DL, CULL, NS>(a->S, a->F, a->px, a->D);
+}
+
 struct PackArgs { const float* depth; const uint8_t* rgb; uint2* out; int W, H; float* tile_max; int* sched; vh::FrameCounters* counters; uint32_t frame; };
 void run_pack(void* p) {
   PackArgs* a = static_cast<PackArgs*>(p);
@@ -53,6 +59,14 @@ void emu_launch_integrate(const StaticParams& S, const FrameParams& F, const uin
     entry = !color ? (cull ? run_variant<false, false, false, false, true> : run_variant<false, false, false, false, false>)
           : fast ? (cull ? run_variant<true, false, false, true, true> : run_variant<true, false, false, true, false>)
                  : (cull ? run_variant<true, false, false, false, true> : run_variant<true, false, false, false, false>);
+  }
+  if (rev == 2) {      // integrate_kernel_r2: 128-thread CTAs with the staging buffers in dynamic shared memory, two steps at a time
+    const bool delta = S.weight_bound <= 65536u;
+    entry = !color ? (cull ? run_r2<false, false, false, true, 2> : run_r2<false, false, false, false, 2>)
+          : delta ? (cull ? run_r2<true, false, true, true, 2> : run_r2<true, false, true, false, 2>)
+                  : (cull ? run_r2<true, false, false, true, 2> : run_r2<true, false, false, false, 2>);
+    emu::run_grid(dim3(std::max(ctas, 1)), dim3(R2_THREADS), entry, &ia, integrate_r2_smem_bytes());
+    return;
   }
   emu::run_grid(dim3(std::max(ctas, 1)), dim3(INT_THREADS), entry, &ia);
 }
@@ -126,6 +140,16 @@ int emu_integrate(emu_integrate_io* io) {
 #undef PICK1
   }
   emu::g_collectives = 0;
+  if (io->variant == 2) {     // integrate_kernel_r2 (bulk-copy staging); two_steps selects the number of steps gated together
+    const bool delta = !io->exact_color && S.weight_bound <= 65536u;
+#define PICK2N(C, V, DL, NS) (io->cull ? run_r2<C, V, DL, true, NS> : run_r2<C, V, DL, false, NS>)
+#define PICK2(C, V, DL) (io->two_steps ? PICK2N(C, V, DL, 2) : PICK2N(C, V, DL, 1))
+    if (io->verify) entry = !color ? PICK2(false, true, false) : delta ? PICK2(true, true, true) : PICK2(true, true, false);
+    else entry = !color ? PICK2(false, false, false) : delta ? PICK2(true, false, true) : PICK2(true, false, false);
+#undef PICK2
+#undef PICK2N
+    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(R2_THREADS), entry, &ia, integrate_r2_smem_bytes());
+  } else
   emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(INT_THREADS), entry, &ia);
   io->voxel_updates = counters.voxel_updates; io->culled = counters.pad[1]; io->mismatch = counters.pad[0];
   io->collectives = emu::g_collectives; io->slow_steps = counters.pad[2]; io->engine_error = engine_error;

@@ -51,7 +51,7 @@ CASE = dict(scene=dict(color=True), vpb=8, vox_size=0.04, trunc=0.2, max_depth=3
 
 
 # kernel revisions (integrate, allocation, marching cubes): 0 = shipped defaults, 1 = opt-in (VH_INTEGRATE_REV / VH_ALLOC_REV / VH_MC_REV = 1)
-@pytest.mark.parametrize("rev,alloc_rev,mc_rev", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
+@pytest.mark.parametrize("rev,alloc_rev,mc_rev", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1), (2, 0, 0), (2, 1, 1)])
 def test_emulated_engine_matches_oracle(vh, ob, synth, rev, alloc_rev, mc_rev):
     nblocks, ntris = run_pair(vh, ob, synth, SMALL, CASE, frames=3, rev=rev, alloc_rev=alloc_rev, mc_rev=mc_rev, num_buckets=1 << 12,
                               pool_blocks=1 << 12, tri_arena_bytes=8 << 20)
@@ -239,7 +239,7 @@ def _random_pose_scene(synth, seed, **kw):
     return RandomPoses(**kw)
 
 
-@pytest.mark.parametrize("seed,revs", [(1, (0, 0, 0)), (2, (1, 1, 1)), (3, (1, 1, 1)), (4, (1, 0, 1)), (5, (0, 1, 0))])
+@pytest.mark.parametrize("seed,revs", [(1, (0, 0, 0)), (2, (1, 1, 1)), (3, (2, 1, 1)), (4, (1, 0, 1)), (5, (0, 1, 0)), (6, (2, 0, 0))])
 def test_emulated_engine_random_rigid_poses(vh, ob, synth, seed, revs):
     """odd image size (not a multiple of the 16-pixel tiles or the 10-pixel ray stride), off-centre principal point,
     random rigid poses; three frames that overlap only by chance"""

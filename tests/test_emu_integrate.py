@@ -52,8 +52,8 @@ def run_case(ob, synth, *, scene_kw, vox, trunc, maxd=3.0, frames=3, color=True,
 SMALL = dict(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=60, spheres=((2.8, 1.5, 1.0, 0.4),), color=True)
 
 
-# kernel revisions: 0 = integrate_kernel (shipped default), 1 = integrate_kernel_r1 (VH_INTEGRATE_REV=1)
-REVS = [0, 1]
+# kernel revisions: 0 = integrate_kernel, 1 = integrate_kernel_r1, 2 = integrate_kernel_r2 (planes staged in shared memory by bulk copies)
+REVS = [0, 1, 2]
 
 
 @pytest.mark.parametrize("rev", REVS)
@@ -74,7 +74,8 @@ def test_emulated_integrate_fine_voxels_discards_blocks(ob, synth, rev):
 
 
 @pytest.mark.parametrize("kernel_kw", [dict(two_steps=1), dict(exact_color=1), dict(verify=1), dict(ctas=1),
-                                       dict(variant=1, exact_color=1), dict(variant=1, verify=1), dict(variant=1, verify=1, exact_color=1)])
+                                       dict(variant=1, exact_color=1), dict(variant=1, verify=1), dict(variant=1, verify=1, exact_color=1),
+                                       dict(variant=2, two_steps=1), dict(variant=2, exact_color=1), dict(variant=2, verify=1, two_steps=1), dict(variant=2, ctas=1)])
 def test_emulated_integrate_variants(ob, synth, kernel_kw):
     run_case(ob, synth, scene_kw=SMALL, vox=0.05, trunc=0.2, frames=2, **kernel_kw)
 
@@ -96,5 +97,5 @@ def test_emulated_integrate_hostile_depth(ob, synth, rev):
         d.reshape(-1)[idx] = bad[rng.randint(0, len(bad), 600)]
         return d
     run_case(ob, synth, scene_kw=SMALL, vox=0.05, trunc=0.2, frames=2, mutate=mutate, variant=rev)
-    if rev == 1:      # NaN / inf numerators leave the fast path: the out-of-line IEEE redo of a step is exercised
+    if rev >= 1:      # NaN / inf numerators leave the fast path: the out-of-line IEEE redo of a step is exercised
         assert run_case.slow_steps > 0

@@ -104,6 +104,33 @@ def test_tombstones_and_table_rebuild(vh, ob, synth):
         check_voxels(e, o, o.all_keys())
 
 
+def test_pool_exhaustion_keeps_the_free_list_and_key_heap_consistent(vh, synth):
+    """inserting past the pool: MAP_POOL_FULL is raised, the lanes without a slot publish the 'pool full' sentinel (not the
+    'not yet published' one a reader would spin on), free_top ends at 0 (never negative), key_heap holds exactly the blocks that
+    got storage; evicting then pushes inside the stack and the freed slots are handed out again (vh_map.cuh:111,123)"""
+    sc = synth.Scene(**SMALL)
+    pool = 40
+    with EmuEngine(engine_params(vh, sc, CASE, num_buckets=1 << 8, pool_blocks=pool, tri_arena_bytes=1 << 20)) as e:
+        keys = np.stack([np.arange(100), np.arange(100) % 7, -np.arange(100)], 1).astype(np.int32)
+        z = np.zeros((len(keys), 512), np.float32)
+        rc = e.upload_blocks(keys, z - 1.0, z + 3.0, np.zeros((len(keys), 512, 3), np.uint8), check=False)
+        assert rc & 2, "MAP_POOL_FULL not raised"
+        assert e.free_slots == 0 and e.num_blocks == pool
+        have = e.get_blocks(keys)[3]
+        assert have.sum() == pool
+        assert key_set(e.all_keys()) == key_set(keys[have]), "key_heap does not list exactly the blocks that got a slot"
+        stored = keys[have]
+        _, _, _, found, released = e.evict_blocks(stored[:10])
+        assert released == 10 and found.all() and e.free_slots == 10 and e.num_blocks == pool - 10
+        fresh = np.array([[500 + i, 1, 2] for i in range(5)], np.int32)
+        e.upload_blocks(fresh, z[:5] + 0.5, z[:5] + 1.0, np.zeros((5, 512, 3), np.uint8), check=False)
+        assert e.free_slots == 5 and e.num_blocks == pool - 5
+        s, w, _, found, neg = e.get_blocks(fresh)
+        assert found.all() and (s == 0.5).all() and (w == 1.0).all() and (neg == 0).all()
+        s, w, _, found, neg = e.get_blocks(stored[10:])
+        assert found.all() and (s == -1.0).all() and (w == 3.0).all() and (neg == 512).all(), "an older block lost its slot"
+
+
 def test_host_residency_rule_matches_oracle(vh, ob, synth):
     """vh_blocks_resident (host arithmetic through the C ABI, no GPU) against the oracle's chunk-candidate test, for blocks all
     over the place and several poses, including chunk-sphere boundary cases at three voxel sizes"""

@@ -16,10 +16,14 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("VH_TEST_REV1") != "1", reason="opt-in kernel revision: set VH_TEST_REV1=1 (tools/gpu_rev1.sh)")]
 
 
-@pytest.fixture(params=["4", "3", "7"], ids=["4ctas", "3ctas", "7x128"])
+# (revision, CTAs per SM, steps gated together): revision 1 = per-lane plane loads after the gate; revision 2 = planes staged in
+# shared memory by bulk async copies (cp.async.bulk + mbarrier)
+@pytest.fixture(params=[("1", "3", "0"), ("1", "4", "0"), ("2", "4", "1"), ("2", "4", "0"), ("2", "3", "1")],
+                ids=["r1-3ctas", "r1-4ctas", "r2-4ctas-2steps", "r2-4ctas-1step", "r2-3ctas-2steps"])
 def rev1(request, monkeypatch):
-    monkeypatch.setenv("VH_INTEGRATE_REV", "1")
-    monkeypatch.setenv("VH_INTEGRATE_CTAS", request.param)
+    monkeypatch.setenv("VH_INTEGRATE_REV", request.param[0])
+    monkeypatch.setenv("VH_INTEGRATE_CTAS", request.param[1])
+    monkeypatch.setenv("VH_INTEGRATE_TWO_STEPS", request.param[2])
 
 
 @pytest.mark.parametrize("name", ["g8_color_holes", "g8_negative_coords"])

@@ -82,6 +82,7 @@ static int free_engine(vh_engine* e) {
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
   }
   for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->ev_mapped_read) cudaEventDestroy(e->ev_mapped_read);
   if (e->h_block) cudaFreeHost(e->h_block);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->upload) cudaStreamDestroy(e->upload);
@@ -113,7 +114,7 @@ static int reset_map(vh_engine* e) {
   CK(cudaMemcpyAsync(D.map.free_top, &nb, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->tombstones = 0;
-  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0; e->forced_syncs = 0; e->integrate_launches = 0;
+  e->frames = 0; e->updates_total = 0; e->max_tris_per_frame = 0; e->known_arena_top = 0; e->frames_in_flight = 0; e->compactions = 0; e->forced_syncs = 0; e->integrate_launches = 0; e->weight_bound_bias = e->weight_bound_env;
   memset(e->h_block, 0, sizeof(*e->h_block));
   return VH_OK;
 }
@@ -143,10 +144,10 @@ int vh_create(const vh_params* p, vh_engine** out) {
   derive_static_params(*p, S);
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && ((v[0] >= '2' && v[0] <= '4') || v[0] == '7')) ? v[0] - '0' : 4; }   // tuning knobs (7: revision 1 only, 7 CTAs of 128 threads)
-  { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
+  { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_env = e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
-  { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] == '1') ? 1 : 0; }
+  { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 0; }
   { const char* v = getenv("VH_ALLOC_REV"); S.alloc_rev = (v && v[0] == '1') ? 1 : 0; }
   { const char* v = getenv("VH_MC_REV"); S.mc_rev = (v && v[0] == '1') ? 1 : 0; }
   static_assert(sizeof(StaticParams) % 16 == 0, "keep the FrameParams behind StaticParams 16-byte aligned in the kernels' parameter blocks");
@@ -215,6 +216,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
          cudaEventCreateWithFlags(&e->ev_rgb[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&e->ev_mapped_read, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { free_engine(e); return fail(VH_ERR_CUDA, "CUDA Error: stream/event creation failed"); }
   {   // tuning knob, off by default: publish the status block from a kernel instead of a D2H copy (see publish_status_kernel)
     const char* v = getenv("VH_STATUS_PUBLISH");
@@ -310,6 +312,10 @@ int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEve
     if (!host_depth_mapped && depth_ready) CK(cudaStreamWaitEvent(e->stream, depth_ready, 0));
     CK(cudaMemsetAsync(D.counters, 0, sizeof(FrameCounters), e->stream));
     launch_alloc_visible(e->S, e->F, host_depth_mapped ? host_depth_mapped : e->cur_depth, D, e->stream);
+    if (host_depth_mapped) {      // the caller's buffer is being read in place on THIS stream: vh_wait_uploads must cover it too
+      CK(cudaEventRecord(e->ev_mapped_read, e->stream));
+      e->mapped_read_pending = true;
+    }
     if (host_depth_mapped && depth_ready) CK(cudaStreamWaitEvent(e->stream, depth_ready, 0));
     if (rgb_ready) CK(cudaStreamWaitEvent(e->stream, rgb_ready, 0));
     launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, D.counters, e->F.frame, e->stream, 1);
@@ -506,6 +512,9 @@ int vh_wait_uploads(vh_engine* e) {
   if (!e) return fail(VH_ERR_INVALID, "null engine");
   CK(cudaSetDevice(e->P.device));
   CK(cudaStreamSynchronize(e->upload));
+  // a ray pass that read the caller's pinned depth buffer in place (synchronous route from an idle GPU) runs on the compute
+  // stream, not on the upload stream: the buffers are reusable only once it has finished as well
+  if (e->mapped_read_pending) { CK(cudaEventSynchronize(e->ev_mapped_read)); e->mapped_read_pending = false; }
   return VH_OK;
 }
 

@@ -35,6 +35,8 @@ struct vh_engine {
   int px_ring = 0;
   cudaEvent_t ev_uploaded[2] = {nullptr, nullptr}, ev_rgb[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   bool buf_used[2] = {false, false};
+  cudaEvent_t ev_mapped_read = nullptr;  // recorded on the compute stream behind a ray pass that read the caller's pinned depth buffer in place
+  bool mapped_read_pending = false;
   int ring = 0;
   const float* cur_depth = nullptr;     // device pointers the stage calls operate on
   const uint8_t* cur_rgb = nullptr;
@@ -55,7 +57,8 @@ struct vh_engine {
   unsigned long long *d_scan_in = nullptr, *d_scan_out = nullptr; void* d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
   uint64_t compactions = 0, forced_syncs = 0;
   uint32_t integrate_launches = 0;      // since the last reset: bounds every voxel weight
-  uint32_t weight_bound_bias = 0;       // env VH_INTEGRATE_EXACT_COLOR=1: pretend weights are large (forces the general colour path)
+  uint32_t weight_bound_bias = 0;       // added to the weight bound: forces the general colour path (env VH_INTEGRATE_EXACT_COLOR=1, or non-integer uploaded weights)
+  uint32_t weight_bound_env = 0;        // the environment's share of it (survives vh_reset)
   int mc_parity = 0;                    // which McQueueCtl slot the next marching-cubes launch uses
   uint32_t tombstones = 0;              // table entries released by vh_evict_blocks since the last rebuild (vh_stream.cu)
   // multi-GPU (vh_shard.cu)

@@ -65,7 +65,7 @@ __global__ void map_erase_kernel(MapView V, const u64* __restrict__ keys, int n,
   if (e >= 0 && atomicCAS(&V.keys[e], key, KEY_TOMB) == key) {
     const int slot = V.slots[e];
     V.slots[e] = -1;
-    if (slot >= 0) { const int pos = atomicAdd(V.free_top, 1); V.free_list[pos] = slot; }
+    if (slot >= 0) map_release_slot(V, slot);
     erased = 1;
   }
   out[i] = erased;

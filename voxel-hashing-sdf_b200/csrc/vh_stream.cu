@@ -48,8 +48,7 @@ __global__ void evict_kernel(const DeviceView D, const u64* __restrict__ keys, i
   }
   if (lane == 0) {
     D.neg_count[slot] = 0; D.tri_count[slot] = 0; D.tri_offset[slot] = 0ull;
-    const int pos = atomicAdd(D.map.free_top, 1);                  // push: the stack only grows here, nothing pops concurrently
-    D.map.free_list[pos] = slot;
+    map_release_slot(D.map, slot);                                 // push: the stack only grows here, nothing pops concurrently
     atomicAdd(released, 1);
   }
 }
@@ -296,9 +295,22 @@ int vh_upload_blocks(vh_engine* e, const int32_t* keys_xyz, int n, const float* 
   if (!e || (n > 0 && (!keys_xyz || !sdf || !weight))) return fail(VH_ERR_INVALID, "null argument");
   if (n <= 0) return VH_OK;
   if (e->shard) return fail(VH_ERR_INVALID, "the out-of-core tier is not available on a sharded map");
+  // The integrate kernel picks its exact short colour averages from an upper bound of every stored weight (launches since the
+  // last reset). Uploaded blocks bring their own weights: they must be finite and non-negative, their maximum joins the
+  // bound, and a weight that is not an integer (never produced by this engine or the reference) switches to the general
+  // colour sequence for good, because the short forms are proven for integer weights only.
+  float max_w = 0.0f; bool integral = true;
+  for (size_t i = 0, m = (size_t)n * BLOCK_VOX; i < m; i++) {
+    const float w = weight[i];
+    if (!(w >= 0.0f) || !std::isfinite(w)) return fail(VH_ERR_INVALID, "vh_upload_blocks: weight[%zu] = %g is negative or not finite", i, (double)w);
+    if (w > max_w) max_w = w;
+    if (w != std::floor(w)) integral = false;
+  }
   std::lock_guard<std::mutex> lk(e->mtx);
   CK(cudaSetDevice(e->P.device));
   CK(cudaStreamSynchronize(e->stream));
+  if (!integral || max_w >= 16777216.0f) e->weight_bound_bias = 1u << 24;
+  else e->integrate_launches = std::max<uint32_t>(e->integrate_launches, (uint32_t)max_w);
   const int CH = 16384;   // blocks per staging round (like vh_download_blocks)
   const int m0 = std::min(n, CH);
   float *d_s = nullptr, *d_w = nullptr; uint8_t* d_c = nullptr; int* d_slots = nullptr;
