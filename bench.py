@@ -52,11 +52,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--config", default=None, choices=["C1", "C2", "C3", "C4"],
+                    help="default: C2 (the headline single-GPU config) at --gpus 1, C4 (room scale, one map sharded over the GPUs) at --gpus > 1")
     ap.add_argument("--no-color", action="store_true")
     ap.add_argument("--no-mc", action="store_true", help="integration only (F_int); default runs working-set MC every frame like the reference")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="--gpus 1: skip the room-scale config 4 side measurement (16 frames on one GPU)")
     ap.add_argument("--ray-steps", type=int, default=0, help="max_ray_steps; 0 = the reference's 100 (configs 3/4: ~1100 reach the walls, SURVEY.md section 8d)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames in one step; 0 = 50 (config 4 with long rays allocates ~0.9 M blocks per frame: use 4)")
     ap.add_argument("--pool-blocks", type=int, default=0, help="voxel-block pool size; 0 = 3 Mi blocks (a long-ray config 4 run needs ~8 Mi)")
@@ -92,22 +94,29 @@ def config_dict(args, cfg, sc, world):
 
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_run(args, frames_wanted, per_step_frames, steps, warmup):
-    """The reference's algorithm on host cores: oracle/vh_oracle.c with all OpenMP threads."""
+    """The reference's algorithm on host cores: oracle/vh_oracle.c with all OpenMP threads (set explicitly: torchrun exports
+    OMP_NUM_THREADS=1 to its children)."""
     from oracle import binding as ob
     synth, cfg, sc = workload(args, 0)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     p = ob.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"], voxels_per_block=8,
-                            use_color=0 if args.no_color else 1, run_mc=0 if args.no_mc else 1, num_threads=0, **ray_kw(args))
+                            use_color=0 if args.no_color else 1, run_mc=0 if args.no_mc else 1, num_threads=ncpu, **ray_kw(args))
+    fresh_map_per_step = args.config == "C4"      # ~0.9 M new blocks (5 GB of host memory) per frame: bounded by starting every step from an empty map
     o = ob.Oracle(p)
-    threads = ob.lib().vo_threads()
+    threads = ncpu
     frames = [sc.frame(i) for i in range(frames_wanted)]
     i = 0
     for _ in range(warmup * per_step_frames):
         o.process_frame(*frames[i % len(frames)]); i += 1
-    t0 = time.perf_counter()
-    n = 0
-    for _ in range(steps * per_step_frames):
-        o.process_frame(*frames[i % len(frames)]); i += 1; n += 1
-    dt = time.perf_counter() - t0
+    n, dt = 0, 0.0
+    for _ in range(steps):
+        if fresh_map_per_step:
+            del o
+            o = ob.Oracle(p)
+        t0 = time.perf_counter()
+        for _ in range(per_step_frames):
+            o.process_frame(*frames[i % len(frames)]); i += 1; n += 1
+        dt += time.perf_counter() - t0
     return n / dt, dt, threads, n
 
 
@@ -326,14 +335,14 @@ def run_ours(args):
 
     # ---- per-kernel profile pass (untimed for the headline): CUDA-event time of every stage of every frame ----
     eng.reset()
-    acc = dict(alloc=0.0, integrate=0.0, mc=0.0, upload=0.0, updates=0, visible=0, tris=0, culled=0)
+    acc = dict(alloc=0.0, integrate=0.0, mc=0.0, cull=0.0, upload=0.0, updates=0, visible=0, tris=0, culled=0)
     per_frame_rows = []          # (frame, ms_integrate, voxel updates, visible blocks, blocks discarded whole)
     for i in frames_of(n_timed):
         eng.integrate_device(dptr(d_depth, i), rgb_dev(i), poses[i])
         s = eng.stats()
-        acc["alloc"] += s.ms_alloc; acc["integrate"] += s.ms_integrate; acc["mc"] += s.ms_mc
+        acc["alloc"] += s.ms_alloc; acc["integrate"] += s.ms_integrate; acc["mc"] += s.ms_mc; acc["cull"] += s.ms_cull
         acc["updates"] += s.voxel_updates; acc["visible"] += s.visible_blocks; acc["tris"] += s.triangles; acc["culled"] += s.culled_blocks
-        per_frame_rows.append((i, s.ms_integrate, s.voxel_updates, s.visible_blocks, s.culled_blocks, s.ms_alloc, s.ms_mc, s.triangles))
+        per_frame_rows.append((i, s.ms_integrate, s.voxel_updates, s.visible_blocks, s.culled_blocks, s.ms_alloc, s.ms_mc, s.triangles, s.ms_cull))
     clocks = sampler.stop() if sampler else None
     st_last = eng.stats()
     allocated = st_last.allocated_blocks
@@ -388,7 +397,7 @@ def run_ours(args):
     dump = os.environ.get("VH_BENCH_DUMP")
     if dump and rank == 0:
         with open(dump, "w") as f:
-            f.write("frame,ms_integrate,voxel_updates,visible_blocks,blocks_discarded,ms_alloc,ms_mc,triangles\n")
+            f.write("frame,ms_integrate,voxel_updates,visible_blocks,blocks_discarded,ms_alloc,ms_mc,triangles,ms_cull\n")
             for r in per_frame_rows:
                 f.write(",".join(str(x) for x in r) + "\n")
     traffic, traffic_src = None, None
@@ -408,13 +417,14 @@ def run_ours(args):
                 "async_value": total_frames / (ms_e2e_async / 1000.0),
                 "async_call": "vh_integrate_async per frame from the same pinned host buffers + one vh_sync: uploads overlap kernels",
                 "u16_async": u16},
-        "gpu_launches": (5 if not args.no_mc else 3) * n_timed,      # pack, allocate, integrate (+ mc_filter, mc_mesh) per frame
+        "gpu_launches": (6 if not args.no_mc else 4) * n_timed + (0 if os.environ.get("VH_STATUS_PUBLISH") == "0" else n_timed)
+                        + (n_timed if os.environ.get("VH_ALLOC_REV") == "2" else 0),      # pack, allocate (1 or 2 kernels), work list, integrate (+ mc_filter, mc_mesh), status per frame
         "voxel_updates_per_sec": sum_over_ranks(float(acc["updates"])) / (ms_value / 1000.0),
-        "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "blocks_discarded_whole_by_integrate": acc["culled"] / n_timed,
+        "per_frame": {"voxel_updates": upd_per_frame, "visible_blocks": vis_per_frame, "blocks_discarded_whole": acc["culled"] / n_timed,
                       "triangles": tris_per_frame,
-                      "ms_alloc": ms_alloc, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated,
+                      "ms_alloc": ms_alloc, "ms_cull_list": acc["cull"] / n_timed, "ms_integrate": ms_int, "ms_mc": ms_mc, "allocated_blocks_end": allocated,
                       "arena_compactions_in_500_frames": int(st_last.arena_compactions)},
-        "roofline": {"kernel": "vh::integrate_kernel_r1" if os.environ.get("VH_INTEGRATE_REV") == "1" else "vh::integrate_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "roofline": {"kernel": "vh::integrate_kernel_staged" if os.environ.get("VH_INTEGRATE_REV") == "2" else "vh::integrate_kernel_direct", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int, "frac_per_frame": frac_frames},
         "roofline_mc": {"kernel": "vh::mc_filter_kernel + vh::mc_mesh_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
@@ -422,24 +432,21 @@ def run_ours(args):
         "clocks": clocks,
         "export": export,
     }
-    if world > 1:
-        # The sharded-map section is an extra on top of the contract's line: if a rank stalls in it (dead peer, NCCL
-        # trouble) every rank gives up after SHARDED_TIMEOUT_S and rank 0 still prints the headline measured above.
-        def give_up():
-            if rank == 0:
-                line["sharded"] = {"error": f"sharded-map section did not finish within {SHARDED_TIMEOUT_S} s; the numbers above were measured before it"}
-                line["cpu_baseline"] = None
-                print(json.dumps(line), flush=True)
-            os._exit(0)
-        dog = threading.Timer(SHARDED_TIMEOUT_S, give_up)
-        dog.daemon = True
-        dog.start()
+    # ---- the room-scale config 4 on this one GPU (the N = 1 point of the multi-GPU curve `bench.py --gpus N` reports) ----
+    if world == 1 and args.config == "C2" and not args.no_c4:
+        eng.close(); eng = None
+        del d_depth, d_rgb, h_depth, h_rgb
+        torch.cuda.empty_cache()
         try:
-            line["sharded"] = run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, poses, n_timed, n_frames, dist, torch)
-        except Exception as ex:      # the peers may be waiting in a collective: the watchdog ends them
-            line["sharded"] = {"error": f"{type(ex).__name__}: {ex}"}
-        dist.barrier()
-        dog.cancel()
+            c4 = synth.CONFIGS["C4"]
+            s4 = synth.make_scene("C4", color=color)
+            fps4 = C4_DEFAULTS["frames_per_step"]
+            line["room_scale"] = dict(single_gpu_run(vh, torch, np, "C4", c4, s4, color, not args.no_mc, local, fps4, 4 * fps4, C4_DEFAULTS["ray_steps"],
+                                                     C4_DEFAULTS["pool_blocks"]), n_gpus=1,
+                                      workload="BASELINE config 4: 640x480, 2 mm voxels, 10 m room centred on the origin, 2^24-bucket x4 hash, trunc 1 cm, "
+                                               "max_ray_steps 1100, first 16 frames (~0.9 M new blocks per frame: the 100-frame map does not fit one GPU)")
+        except Exception as ex:
+            line["room_scale"] = {"error": f"{type(ex).__name__}: {ex}"}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             fps, dt, threads, n = cpu_reference_run(args, args.cpu_frames, 1, args.cpu_frames, 0)
@@ -448,71 +455,260 @@ def run_ours(args):
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_sharded(args, vh, sc, cfg, color, rank, world, local, h_depth, h_rgb, poses, n_timed, n_frames, dist, torch):
-    """ONE map sharded over the GPUs by block hash (BASELINE config 4 style) on rank 0's sequence: NCCL broadcast of every
-    frame from rank 0's pinned host buffers, each GPU allocates/integrates/meshes its own blocks, marching-cubes halos are
-    read from the owner GPU over NVLink. Strong scaling: total work fixed. Timed end to end (host buffers on rank 0)."""
-    import numpy as np
-    p_all = torch.from_numpy(poses.copy()).cuda()
-    dist.broadcast(p_all, src=0)                     # every rank integrates rank 0's trajectory
-    poses0 = p_all.cpu().numpy()
-    out = {}
-    for label, mc in (("integrate_only", 0), ("with_marching_cubes", 1)):
-        p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"],
-                                num_buckets=cfg["num_buckets"], entries_per_bucket=4, pool_blocks=(args.pool_blocks or (3 << 20)) // world + (1 << 18),
-                                use_color=1 if color else 0, mc_per_frame=mc, device=local, shard_rank=rank, shard_count=world,
-                                tri_arena_bytes=(4 << 30) // world + (1 << 30), **ray_kw(args))
-        eng = vh.TsdfEngine(p)
-        ids = [vh.TsdfEngine.shard_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        eng.shard_connect(ids[0])
-        stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+# ---------------------------------------------------------------------------------------------------------------------
+def peak_hbm():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-        def one_pass(n):
-            for i in [k % n_frames for k in range(n)]:
-                if rank == 0:
-                    eng.integrate_sharded(h_depth[i].data_ptr(), h_rgb[i].data_ptr() if color else None, poses0[i])
-                else:
-                    eng.integrate_sharded(None, None, poses0[i])
-            eng.sync()
-        one_pass(min(n_timed, 3 * FRAMES_PER_STEP))      # warm-up
-        eng.reset()
-        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        one_pass(n_timed)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1000.0
-        dist.barrier()
-        t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        # counters of the whole sequence: replay with per-frame group stats is too slow; use totals from the checksum
-        cs = eng.checksum()
-        u = torch.tensor([cs["sum_w"]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(u, op=dist.ReduceOp.SUM)
-        st = eng.shard_stats()
-        out[label] = {"frames_per_sec": n_timed / (ms / 1000.0), "voxel_updates_per_sec": float(u.item()) / (ms / 1000.0),
-                      "ms_per_frame": ms / n_timed, "allocated_blocks_all_shards": int(st.allocated_blocks)}
-        eng.close()
-    out["note"] = ("single map, owner(block) = hash(block's 8^3-block cube) mod n_gpus; per frame one ncclBroadcast of pose+depth+rgb from rank 0 "
-                   "(pinned host buffers), replicated ray pass, marching-cubes halos read from the owner GPU over NVLink between two flag "
-                   "barriers; strong scaling (same 500-frame sequence at every n_gpus)")
+
+def make_frames(torch, np, sc, n_frames, color, pinned=True, device=True):
+    H, W = sc.height, sc.width
+    h_depth = torch.empty((n_frames, H, W), dtype=torch.float32)
+    h_rgb = torch.empty((n_frames, H, W, 3), dtype=torch.uint8)
+    if pinned:
+        h_depth, h_rgb = h_depth.pin_memory(), h_rgb.pin_memory()
+    poses = np.zeros((n_frames, 16), np.float32)
+    for i in range(n_frames):
+        d, rgb, c2w = sc.frame(i)
+        h_depth[i] = torch.from_numpy(d); h_rgb[i] = torch.from_numpy(rgb); poses[i] = c2w
+    d_depth = h_depth.cuda() if device else None
+    d_rgb = h_rgb.cuda() if device else None
+    return h_depth, h_rgb, d_depth, d_rgb, poses
+
+
+def single_gpu_run(vh, torch, np, cfg_name, cfg, sc, color, mc, local, n_warm, n_timed, ray_steps, pool_blocks, frames=None):
+    """One map on ONE GPU, frames resident in its HBM: frames/s, voxel updates/s and the per-stage times (used for config 4 at
+    --gpus 1 and, on rank 0, as the same-run single-GPU point of a multi-GPU run)."""
+    n_frames = min(max(n_timed, n_warm), sc.n_frames)
+    if frames is None:
+        frames = make_frames(torch, np, sc, n_frames, color, pinned=False)
+    _, _, d_depth, d_rgb, poses = frames
+    p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"], num_buckets=cfg["num_buckets"],
+                            entries_per_bucket=4, pool_blocks=pool_blocks, use_color=1 if color else 0, mc_per_frame=1 if mc else 0, device=local,
+                            tri_arena_bytes=4 << 30, **(dict(max_ray_steps=ray_steps) if ray_steps else {}))
+    eng = vh.TsdfEngine(p)
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    rgbp = (lambda i: d_rgb[i].data_ptr()) if color else (lambda i: None)
+    for k in range(n_warm):
+        i = k % n_frames
+        eng.integrate_device(d_depth[i].data_ptr(), rgbp(i), poses[i])
+    eng.sync()
+    eng.reset()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(n_timed):
+        i = k % n_frames
+        eng.integrate_device(d_depth[i].data_ptr(), rgbp(i), poses[i])
+    e1.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    updates_total = eng.stats().voxel_updates_total
+    allocated = eng.stats().allocated_blocks
+    # per-stage pass (untimed for the figures above)
+    eng.reset()
+    acc = dict(alloc=0.0, cull=0.0, integrate=0.0, mc=0.0, updates=0, visible=0, culled=0, tris=0)
+    for k in range(n_timed):
+        i = k % n_frames
+        eng.integrate_device(d_depth[i].data_ptr(), rgbp(i), poses[i])
+        st = eng.stats()
+        acc["alloc"] += st.ms_alloc; acc["cull"] += st.ms_cull; acc["integrate"] += st.ms_integrate; acc["mc"] += st.ms_mc
+        acc["updates"] += st.voxel_updates; acc["visible"] += st.visible_blocks; acc["culled"] += st.culled_blocks; acc["tris"] += st.triangles
+    eng.close()
+    W, H = sc.width, sc.height
+    u, v = acc["updates"] / n_timed, acc["visible"] / n_timed
+    bytes_int = 16.0 * u + 4.0 * W * H + 12.0 * v + ((8.0 * u + 3.0 * W * H) if color else 0.0)
+    ms_int = acc["integrate"] / n_timed
+    peak, _ = peak_hbm()
+    return {"frames_per_sec": n_timed / (ms / 1000.0), "voxel_updates_per_sec": updates_total / (ms / 1000.0), "ms_per_frame": ms / n_timed, "frames": n_timed,
+            "allocated_blocks_end": int(allocated),
+            "per_frame": {"voxel_updates": u, "visible_blocks": v, "blocks_discarded_whole": acc["culled"] / n_timed, "triangles": acc["tris"] / n_timed,
+                          "ms_alloc": acc["alloc"] / n_timed, "ms_cull_list": acc["cull"] / n_timed, "ms_integrate": ms_int, "ms_mc": acc["mc"] / n_timed},
+            "integrate_roofline_frac": (bytes_int / (ms_int * 1e-3) / 1e9 / peak) if ms_int > 0 else None}
+
+
+def sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_warm, n_timed, ray_steps, pool_blocks, frames, host_inputs):
+    """ONE map sharded over the GPUs by block hash on rank 0's sequence (north_star's multi-GPU path): per frame rank 0 puts
+    the frame into its ring (device copy, or H2D from pinned host buffers when host_inputs), every GPU packs it out of rank 0's
+    memory over NVLink, marches its share of the rays, sends block keys to their owners, integrates and meshes its own blocks.
+    Strong scaling: the work is fixed. Device time = max over ranks of the CUDA-event time on the engine's stream (and of the wall
+    clock of the enqueue loop, whichever is larger)."""
+    h_depth, h_rgb, d_depth, d_rgb, poses = frames
+    n_frames = len(poses)
+    p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"], num_buckets=cfg["num_buckets"],
+                            entries_per_bucket=4, pool_blocks=pool_blocks // world + (1 << 19), use_color=1 if color else 0, mc_per_frame=1 if mc else 0,
+                            device=local, shard_rank=rank, shard_count=world, tri_arena_bytes=(4 << 30) // world + (1 << 30),
+                            **(dict(max_ray_steps=ray_steps) if ray_steps else {}))
+    eng = vh.TsdfEngine(p)
+    ids = [vh.TsdfEngine.shard_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    eng.shard_connect(ids[0])
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+
+    def one_pass(n):
+        for k in range(n):
+            i = k % n_frames
+            if rank != 0:
+                eng.integrate_sharded_device(None, None, poses[i])
+            elif host_inputs:
+                eng.integrate_sharded(h_depth[i].data_ptr(), h_rgb[i].data_ptr() if color else None, poses[i])
+            else:
+                eng.integrate_sharded_device(d_depth[i].data_ptr(), d_rgb[i].data_ptr() if color else None, poses[i])
+        eng.sync()
+    one_pass(n_warm)
+    eng.reset()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    one_pass(n_timed)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1000.0
+    dist.barrier()
+    t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    mine = eng.stats()
+    u = torch.tensor([float(mine.voxel_updates_total), float(mine.allocated_blocks), float(mine.allocated_blocks)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(u[:2], op=dist.ReduceOp.SUM)
+    dist.all_reduce(u[2:], op=dist.ReduceOp.MAX)
+    out = {"frames_per_sec": n_timed / (ms / 1000.0), "voxel_updates_per_sec": float(u[0].item()) / (ms / 1000.0), "ms_per_frame": ms / n_timed, "frames": n_timed,
+           "allocated_blocks_all_shards": int(u[1].item()), "allocated_blocks_largest_shard": int(u[2].item()),
+           "last_frame_this_rank": {"ms_alloc": mine.ms_alloc, "ms_cull_list": mine.ms_cull, "ms_integrate": mine.ms_integrate, "ms_mc": mine.ms_mc}}
+    dist.barrier()
+    eng.close()
     return out
+
+
+def run_multi(args):
+    """--gpus N > 1 (torchrun, one process per GPU): `value` = frames/s of ONE map sharded over the N GPUs (default: the room-scale
+    config 4, "scaling": "strong"); side keys: the same workload on one GPU in the same run (rank 0), the headline config 2 sharded,
+    and config 5 (independent maps, one per GPU)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    vh = importlib.import_module("voxel-hashing-sdf_b200")
+    synth = importlib.import_module("voxel-hashing-sdf_b200.synth")
+    color, mc = not args.no_color, not args.no_mc
+    cfg = synth.CONFIGS[args.config]
+    sc = synth.make_scene(args.config, color=color)               # every rank integrates rank 0's trajectory
+    n_timed, n_warm = args.steps * FRAMES_PER_STEP, args.warmup * FRAMES_PER_STEP
+    n_frames = min(max(n_timed, n_warm), sc.n_frames)
+    pool = args.pool_blocks or (3 << 20)
+    frames = make_frames(torch, np, sc, n_frames, color, pinned=(rank == 0), device=(rank == 0))
+    sampler = ClockSampler(local) if rank == 0 else None
+    main = sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_warm, n_timed, args.ray_steps, pool, frames, host_inputs=False)
+    e2e = sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, min(n_warm, FRAMES_PER_STEP), n_timed, args.ray_steps, pool, frames, host_inputs=True)
+    clocks = sampler.stop() if sampler else None
+    side = {}
+
+    def guarded(name, fn):        # an auxiliary measurement never costs the headline
+        try:
+            side[name] = fn()
+        except Exception as ex:
+            side[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        dist.barrier()
+
+    # the same workload on ONE GPU in the same run (rank 0; the other ranks wait): the N = 1 point of this curve
+    def single():
+        if rank != 0:
+            return None
+        return single_gpu_run(vh, torch, np, args.config, cfg, sc, color, mc, local, n_warm, n_timed, args.ray_steps, pool, frames=frames)
+    guarded("single_gpu_same_run", single)
+    if args.config != "C2":       # the headline config sharded the same way: a 0.2 ms frame, latency-bound
+        def c2():
+            c = synth.CONFIGS["C2"]
+            s2 = synth.make_scene("C2", color=color)
+            f2 = make_frames(torch, np, s2, 100, color, pinned=(rank == 0), device=(rank == 0))
+            return sharded_run(vh, torch, np, dist, c, s2, color, mc, rank, world, local, 50, 100, 0, 3 << 20, f2, host_inputs=False)
+        guarded("headline_c2_sharded", c2)
+    # BASELINE config 5: one independent 640x480 / 5 mm sequence and map per GPU (phase-shifted trajectories), no data-path collective
+    def replicas():
+        c = synth.CONFIGS["C2"]
+        s5 = synth.make_scene("C2", color=color, phase=0.37 * rank)
+        r = single_gpu_run(vh, torch, np, "C2", c, s5, color, mc, local, 50, 150, 0, 3 << 20)
+        t = torch.tensor([r["ms_per_frame"] * r["frames"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"frames_per_sec_all_gpus": world * r["frames"] / (float(t.item()) / 1000.0), "frames_per_gpu": r["frames"], "scaling": "weak"}
+    guarded("config5_independent_maps", replicas)
+
+    if rank == 0:
+        W, H = sc.width, sc.height
+        h2d = W * H * 4 + (W * H * 3 if color else 0) + 64
+        nkern = 7 + (3 if mc else 0)      # frame wait/ready, pack, ray keys, barrier, insert, work list, integrate (+ barrier, mc filter, mc mesh), status
+        line = {
+            "metric": METRIC, "value": main["frames_per_sec"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_frame"] * FRAMES_PER_STEP, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(config_dict(args, cfg, sc, world), multi_gpu="ONE map sharded by block-coordinate hash (owner = hash of the block's 8^3-block cube mod n_gpus): "
+                           "rank 0's frame read by every GPU's pack kernel over NVLink, rays split across the GPUs, keys sent to their owners' inboxes, "
+                           "every GPU integrates and meshes its own blocks (marching-cubes halos read from the owner GPU), two flag barriers per frame",
+                           note="at --gpus 1 the line's workload is BASELINE config 2 (metric depth_frames_per_sec_640x480_5mm); this line's N = 1 point is "
+                                "room_scale.single_gpu_same_run (the same frames on one GPU in the same run)"),
+            "voxel_updates_per_sec": main["voxel_updates_per_sec"],
+            "e2e": {"value": e2e["frames_per_sec"], "unit": UNIT, "h2d_bytes_per_step": h2d * FRAMES_PER_STEP, "d2h_bytes_per_step": 128 * FRAMES_PER_STEP * world,
+                    "call": "vh_integrate_sharded per frame: pinned host depth+rgb on rank 0 -> H2D into rank 0's frame ring (upload stream) -> every GPU; one vh_sync at the end"},
+            "gpu_launches": nkern * n_timed * world,
+            "sharded": main, "sharded_e2e": e2e,
+            "room_scale" if args.config == "C4" else "curve": {"n_gpus": world, "frames_per_sec": main["frames_per_sec"], "voxel_updates_per_sec": main["voxel_updates_per_sec"],
+                                                              "single_gpu_same_run": side.get("single_gpu_same_run")},
+            "headline_c2_sharded": side.get("headline_c2_sharded"),
+            "config5_independent_maps": side.get("config5_independent_maps"),
+            "roofline": None, "cpu_baseline": None, "clocks": clocks,
+        }
+        sg = side.get("single_gpu_same_run") or {}
+        if sg.get("per_frame"):
+            peak, peak_src = peak_hbm()
+            pf = sg["per_frame"]
+            b = 16.0 * pf["voxel_updates"] + 4.0 * W * H + 12.0 * pf["visible_blocks"] + ((8.0 * pf["voxel_updates"] + 3.0 * W * H) if color else 0.0)
+            ach = b / (pf["ms_integrate"] * 1e-3) / 1e9
+            line["roofline"] = {"kernel": "vh::integrate_kernel_direct" if os.environ.get("VH_INTEGRATE_REV") == "1" else "vh::integrate_kernel_staged",
+                                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                                "algorithmic_bytes_per_launch": b, "avg_launch_ms": pf["ms_integrate"], "measured_on": "one GPU, whole map (single_gpu_same_run)"}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+C4_DEFAULTS = dict(ray_steps=1100, frames_per_step=4, pool_blocks=16 << 20)    # room scale: the step cap scaled to the block size, ~0.9 M new blocks per frame
+
+
+def apply_defaults(a):
+    """--gpus 1: BASELINE config 2 (headline). --gpus N > 1: BASELINE config 4 (room scale, ONE map sharded over the GPUs)."""
+    global FRAMES_PER_STEP, METRIC
+    if a.config is None:
+        a.config = "C2" if a.gpus <= 1 else "C4"
+    if a.config == "C4":
+        a.ray_steps = a.ray_steps or C4_DEFAULTS["ray_steps"]
+        a.frames_per_step = a.frames_per_step or C4_DEFAULTS["frames_per_step"]
+        a.pool_blocks = a.pool_blocks or C4_DEFAULTS["pool_blocks"]
+        METRIC = "depth_frames_per_sec_640x480_2mm_room_scale"
+    elif a.config != "C2":
+        METRIC = f"depth_frames_per_sec_{a.config}"
+    if a.frames_per_step > 0:
+        FRAMES_PER_STEP = a.frames_per_step
 
 
 if __name__ == "__main__":
     a = parse()
-    if a.frames_per_step > 0:
-        FRAMES_PER_STEP = a.frames_per_step
+    apply_defaults(a)
     if a.impl == "reference":
         run_reference_arm(a)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_multi(a)
     else:
         run_ours(a)

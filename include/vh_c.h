@@ -85,7 +85,9 @@ typedef struct vh_stats {
   uint64_t debug_mismatches;    /* with env VH_INTEGRATE_VERIFY=1: fast-path vs IEEE-path disagreements in the last frame (must be 0) */
   uint64_t arena_compactions;   /* times the triangle arena was compacted (superseded per-block meshes dropped) */
   uint64_t forced_syncs;        /* times an asynchronous call had to drain the stream to bound arena use */
-  uint64_t culled_blocks;       /* visible blocks of the last frame the integrate kernel discarded whole (provably no update) */
+  uint64_t culled_blocks;       /* visible blocks of the last frame discarded whole before integration (provably no update) */
+  float ms_cull;                /* CUDA-event time of the pass that builds integrate's work list (whole-block discard); not part of ms_alloc / ms_integrate */
+  float reserved_f;
 } vh_stats;
 
 /* vertex layout of the triangle soup: the reference's Vertex (tsdf.cuh:65-77), 16 bytes */
@@ -166,6 +168,8 @@ VH_API int vh_owner_of_block(int x, int y, int z, int shard_count, int shard_gro
 VH_API int vh_shard_unique_id(uint8_t id[VH_NCCL_ID_BYTES]);
 VH_API int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]);
 VH_API int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w);
+VH_API int vh_integrate_sharded_device(vh_engine* e, const float* d_depth, const uint8_t* d_rgb, const float* c2w);   /* frame resident in rank 0's HBM */
+VH_API int vh_shard_barrier(vh_engine* e);        /* collective, stream-ordered: every GPU has finished what was enqueued before it */
 VH_API int vh_shard_gather_mesh(vh_engine* e, int mode, vh_triangle* out, uint64_t cap, uint64_t* n);
 VH_API int vh_shard_stats(vh_engine* e, vh_stats* sum);
 /* host-only helper of the gather: merge per-shard block lists (each in mesh order) into the global mesh order */

@@ -100,6 +100,7 @@ class EmuEngine:
         L.emu_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_phase_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_phase_mc.argtypes = [C.c_void_p]
+        L.emu_phase_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_connect.argtypes = [C.c_void_p, C.c_int]
         L.emu_last_updates.restype = C.c_ulonglong
         L.emu_last_triangles.restype = C.c_ulonglong
@@ -142,6 +143,12 @@ class EmuEngine:
         rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
         rc = self.L.emu_phase_integrate(self.h, depth.ctypes.data, None if rgb is None else rgb.ctypes.data, c2w.ctypes.data)
         assert rc == 0, f"map/engine error flags 0x{rc:x}"
+
+    def phase_keys(self, depth, c2w):
+        depth = np.ascontiguousarray(depth, np.float32)
+        c2w = np.ascontiguousarray(c2w, np.float32)
+        rc = self.L.emu_phase_keys(self.h, depth.ctypes.data, c2w.ctypes.data)
+        assert rc == 0, f"map error flags 0x{rc:x}"
 
     def phase_mc(self):
         rc = self.L.emu_phase_mc(self.h)
@@ -250,6 +257,8 @@ class EmuGroup:
         self.close()
 
     def process_frame(self, depth, rgb, c2w):
+        for e in self.ranks:              # allocation revision 2: every rank routes its share of the rays' keys, then the frame barrier
+            e.phase_keys(depth, c2w)
         for e in self.ranks:
             e.phase_integrate(depth, rgb, c2w)
         for e in self.ranks:

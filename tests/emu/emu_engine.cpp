@@ -29,6 +29,10 @@ struct emu_engine {
   std::vector<float> sdf, wgt, tile_max;
   std::vector<uchar4> rgb;
   std::vector<McWork> mc_queue;
+  std::vector<uint4> work;
+  std::vector<u64> inbox;
+  int inbox_count[4] = {0, 0, 0, 0};
+  int keys_done = 0;             // ray_keys_kernel of the current frame has run (emu_phase_keys)
   std::vector<vh_triangle> arena;
   std::vector<unsigned long long> tri_offset;
   std::vector<uint2> px;
@@ -51,15 +55,15 @@ namespace {
 struct AllocArgs { StaticParams S; FrameParams F; const float* depth; DeviceView D; int tiles_x; };
 void run_alloc(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel(a->S, a->F, a->depth, a->D, a->tiles_x); }
 void run_alloc_r1(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel_r1(a->S, a->F, a->depth, a->D, a->tiles_x); }
+struct KeysArgs { StaticParams S; FrameParams F; const float* depth; DeviceView D; int tiles_x, n_tiles; };
+template <int TRX, int TRY> void run_ray_keys(void* p) { KeysArgs* a = static_cast<KeysArgs*>(p); ray_keys_kernel<TRX, TRY>(a->S, a->F, a->depth, a->D, a->tiles_x, a->n_tiles); }
+struct InsertArgs { DeviceView D; uint32_t frame; };
+void run_insert_keys(void* p) { InsertArgs* a = static_cast<InsertArgs*>(p); insert_keys_kernel(a->D, a->frame); }
 struct McArgs { StaticParams S; uint32_t frame; DeviceView D; const int* list; const int* list_count; int full_map; unsigned long long* out_offset; int* out_count;
                 McWork* queue; McQueueCtl* ctl; McQueueCtl* ctl_next; const uint4* tables; };
 void run_filter_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_mesh_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
-void run_filter_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false, 1>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
-void run_filter_sharded_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true, 1>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
 void run_filter(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
-void run_mesh_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false, 1>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
-void run_mesh_sharded_r1(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true, 1>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 // test-only kernel: the step-by-step DDA (ray_march) and the merge formulation (merge_fill_keys) of the same tile of rays,
 // compared key by key; out[0] += mismatching steps, out[1] += steps compared, out[2] += non-empty keys
@@ -123,9 +127,11 @@ emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exac
   e->free_top = (int)nb; e->key_heap.assign(nb, 0);
   e->sdf.assign(nb * BLOCK_VOX, 0.0f); e->wgt.assign(nb * BLOCK_VOX, 0.0f);
   if (S.use_color) e->rgb.assign(nb * BLOCK_VOX, uchar4{0, 0, 0, 0});
-  e->neg_count.assign(nb, 0); e->sched.assign(8 * 32, 0);
+  e->neg_count.assign(nb, 0); e->sched.assign(9 * 32, 0);
   e->tile_max.assign((size_t)((p->width + 15) / 16) * ((p->height + 15) / 16), 0.0f);
-  e->visible.assign(D.list_cap, 0); e->mc_queue.resize(D.list_cap);
+  e->visible.assign(D.list_cap, 0); e->mc_queue.resize(D.list_cap); e->work.resize(D.list_cap);
+  D.inbox_cap = (int)std::max<size_t>(rays * (size_t)S.max_steps, 1024);
+  e->inbox.assign(2 * (size_t)D.inbox_cap, 0);
   e->arena.resize(std::max<size_t>((size_t)p->tri_arena_bytes / sizeof(vh_triangle), 1024));
   e->tri_offset.assign(nb, 0); e->tri_count.assign(nb, 0);
   e->px.assign((size_t)p->width * p->height + 1, make_uint2(0u, 0u));                          // + the sentinel record
@@ -140,7 +146,7 @@ emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exac
   D.map.free_top = &e->free_top; D.map.key_heap = e->key_heap.data(); D.map.heap_counter = &e->heap_counter; D.map.error_flag = &e->map_error;
   D.map.num_blocks = p->pool_blocks;
   D.stamps = e->stamps.data(); D.sdf = e->sdf.data(); D.wgt = e->wgt.data(); D.rgb = S.use_color ? e->rgb.data() : nullptr;
-  D.sched = e->sched.data(); D.tile_max = e->tile_max.data(); D.neg_count = e->neg_count.data(); D.visible = e->visible.data();
+  D.sched = e->sched.data(); D.work = e->work.data(); D.inbox = e->inbox.data(); D.inbox_count = e->inbox_count; D.inbox_done = e->inbox_count + 2; D.tile_max = e->tile_max.data(); D.neg_count = e->neg_count.data(); D.visible = e->visible.data();
   D.counters = &e->counters; D.arena = e->arena.data(); D.arena_top = &e->arena_top; D.arena_cap = e->arena.size();
   D.tri_offset = e->tri_offset.data(); D.tri_count = e->tri_count.data(); D.engine_error = &e->engine_error; D.overflow_frame = &e->overflow_frame;
   D.updates_total = &e->updates_total; D.peers = nullptr; D.mc_queue = e->mc_queue.data(); D.mc_ctl = e->mc_ctl; D.mc_parity = &e->mc_parity;
@@ -152,13 +158,42 @@ void emu_destroy(emu_engine* e) { delete e; }
 // One frame in two phases. Single map: the order of enqueue_stages for frames resident on the device — pack (resets the
 // counters), allocate, integrate; then marching cubes over the visible list. Sharded map (vh_integrate_sharded): every
 // rank runs phase 1 on the broadcast frame, a barrier, every rank runs phase 2 reading its peers' tables and planes.
-int emu_phase_integrate(emu_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
-  const StaticParams& S = e->S; DeviceView& D = e->D;
+// allocation revision 2, first half (launch_ray_keys): the frame's keys into their owners' inboxes. On a sharded map every rank
+// runs this before any rank inserts (the frame barrier of vh_integrate_sharded); tile shapes alternate between frames.
+static void emu_begin_frame(emu_engine* e, const float* c2w) {
   derive_frame_params(e->P, e->S, c2w, e->F);
   e->F.frame = (uint32_t)(++e->frames);
+}
+static void emu_ray_keys(emu_engine* e, const float* depth) {
+  const StaticParams& S = e->S;
+  const int shape = (int)(e->frames % 3);
+  const int trx = shape == 0 ? 4 : 2, try_ = shape == 2 ? 1 : 2;
+  const int tiles_x = (S.nrx + trx - 1) / trx, tiles_y = (S.nry + try_ - 1) / try_, n_tiles = tiles_x * tiles_y;
+  const bool routed = S.shard_count > 1 && e->D.peers != nullptr;
+  const int grid = routed ? (n_tiles + (int)S.shard_count - 1) / (int)S.shard_count : n_tiles;
+  KeysArgs a{S, e->F, depth, e->D, tiles_x, n_tiles};
+  const size_t smem = ray_keys_smem_bytes(S.max_steps, trx * try_);
+  emu::run_grid(dim3(grid), dim3(KEYS_THREADS), shape == 0 ? run_ray_keys<4, 2> : shape == 1 ? run_ray_keys<2, 2> : run_ray_keys<2, 1>, &a, smem);
+}
+int emu_phase_keys(emu_engine* e, const float* depth, const float* c2w) {
+  if (e->alloc_rev != 2) return 0;
+  emu_begin_frame(e, c2w);
+  emu_ray_keys(e, depth);
+  e->keys_done = 1;
+  return e->map_error;
+}
+
+int emu_phase_integrate(emu_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+  const StaticParams& S = e->S; DeviceView& D = e->D;
+  if (!e->keys_done) emu_begin_frame(e, c2w);
   const uint8_t* rgb_in = S.use_color ? rgb : nullptr;
   emu_launch_pack(depth, rgb_in, e->px.data(), S.W, S.H, D.tile_max, D.sched, D.counters, e->F.frame);
-  {
+  if (e->alloc_rev == 2) {
+    if (!e->keys_done) emu_ray_keys(e, depth);
+    e->keys_done = 0;
+    InsertArgs ia{D, e->F.frame};
+    emu::run_grid(dim3(3), dim3(INSERT_THREADS), run_insert_keys, &ia);                          // launch_insert_keys
+  } else {
     const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;     // launch_alloc_visible
     const size_t smem = 2 * CHUNK_KEYS * sizeof(u64) + (size_t)S.max_steps * RAYS * sizeof(int);
     AllocArgs a{S, e->F, depth, D, tiles_x};
@@ -178,10 +213,8 @@ int emu_phase_mc(emu_engine* e) {
     e->mc_parity ^= 1;
     McArgs m{S, e->F.frame, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, D.mc_queue, ctl, ctl_next, e->tables.data()};
     const bool sharded = S.shard_count > 1 && D.peers;
-    if (S.mc_rev == 1) emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded_r1 : run_filter_r1, &m);
-    else emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
-    if (S.mc_rev == 1) emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded_r1 : run_mesh_r1, &m);
-    else emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
+    emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
+    emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
   }
   return e->map_error | (e->engine_error << 8);
 }
@@ -208,8 +241,8 @@ long long emu_full_map_mc(emu_engine* e) {
   e->mc_parity ^= 1;
   McArgs m{S, e->F.frame, D, e->full_list.data(), &count, 1, e->full_off.data(), e->full_cnt.data(), D.mc_queue, ctl, ctl_next, e->tables.data()};
   const bool sharded = S.shard_count > 1 && D.peers;
-  if (S.mc_rev == 1) { emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded_r1 : run_filter_r1, &m); emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded_r1 : run_mesh_r1, &m); }
-  else { emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m); emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m); }
+  emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
+  emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
   long long t = 0;
   for (int i = 0; i < nb; i++) t += e->full_cnt[i];
   e->full_valid = 1;
@@ -297,7 +330,7 @@ int emu_connect(emu_engine** ranks, int n) {
     for (int q = 0; q < n; q++) {
       const DeviceView& Q = ranks[q]->D;
       T.v[q].keys = Q.map.keys; T.v[q].slots = Q.map.slots; T.v[q].stamps = Q.stamps; T.v[q].neg_count = Q.neg_count; T.v[q].sdf = Q.sdf; T.v[q].rgb = Q.rgb;
-      T.v[q].mask = Q.map.mask;
+      T.v[q].mask = Q.map.mask; T.v[q].inbox = Q.inbox; T.v[q].inbox_count = Q.inbox_count;
     }
     ranks[r]->D.peers = &ranks[r]->peers;
   }

@@ -10,22 +10,24 @@ namespace {
 
 struct IntegrateArgs { vh::StaticParams S; vh::FrameParams F; const uint2* px; vh::DeviceView D; int variant; };
 
-template <bool C, bool V, bool T, bool Q, bool CULL>
-void run_variant(void* p) {
+template <bool C, bool V, bool DL, int M>
+void run_direct(void* p) {
   IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
-  vh::integrate_kernel<C, V, 4, T, Q, true, CULL>(a->S, a->F, a->px, a->D);
+  vh::integrate_kernel_direct<C, V, DL, M, false>(a->S, a->F, a->px, a->D);
 }
-
-template <bool C, bool V, bool DL, bool CULL>
-void run_r1(void* p) {
+template <bool C, bool V, bool DL>
+void run_direct_wide(void* p) {      // 64-bit voxel indices (pools beyond 2^23 blocks)
   IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
-  vh::integrate_kernel_r1<C, V, DL, CULL, 4>(a->S, a->F, a->px, a->D);
+  vh::integrate_kernel_direct<C, V, DL, 3, true>(a->S, a->F, a->px, a->D);
 }
-
-template <bool C, bool V, bool DL, bool CULL, int NS>
-void run_r2(void* p) {
+template <bool C, bool V, bool DL, int NS>
+void run_staged(void* p) {
   IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
-  vh::integrate_kernel_r2<C, V, DL, CULL, NS>(a->S, a->F, a->px, a->D);
+  vh::integrate_kernel_staged<C, V, DL, NS, 4>(a->S, a->F, a->px, a->D);
+}
+void run_cull_list(void* p) {
+  IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
+  vh::cull_list_kernel(a->S, a->F, a->D);
 }
 
 struct PackArgs { const float* depth; const uint8_t* rgb; uint2* out; int W, H; float* tile_max; int* sched; vh::FrameCounters* counters; uint32_t frame; };
@@ -43,32 +45,19 @@ void emu_launch_pack(const float* depth, const uint8_t* rgb, uint2* out, int W, 
   emu::run_grid(dim3((W + 15) / 16, (H + 15) / 16), dim3(16, 16), run_pack, &pa);
 }
 
-// dispatch of launch_integrate (csrc/vh_integrate.cu) for the default tuning (one step at a time, 4 CTAs per SM), on `ctas` emulated CTAs
+// launch_cull_list + launch_integrate (csrc/vh_integrate.cu) on `ctas` emulated CTAs; rev 2 = staged (two steps at a time), else direct
 void emu_launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* px, const DeviceView& D, bool color, int rev, int ctas) {
   color = color && S.use_color;
   IntegrateArgs ia{S, F, px, D, rev};
-  const bool cull = S.integrate_cull != 0;
-  void (*entry)(void*) = nullptr;
-  if (rev == 1) {
-    const bool delta = S.weight_bound <= 65536u;
-    entry = !color ? (cull ? run_r1<false, false, false, true> : run_r1<false, false, false, false>)
-          : delta ? (cull ? run_r1<true, false, true, true> : run_r1<true, false, true, false>)
-                  : (cull ? run_r1<true, false, false, true> : run_r1<true, false, false, false>);
+  const bool delta = S.weight_bound <= 65536u;
+  emu::run_grid(dim3(2), dim3(256), run_cull_list, &ia);
+  if (rev == 2) {
+    void (*entry)(void*) = !color ? run_staged<false, false, false, 2> : delta ? run_staged<true, false, true, 2> : run_staged<true, false, false, 2>;
+    emu::run_grid(dim3(std::max(ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes());
   } else {
-    const bool fast = S.weight_bound <= 4096u;
-    entry = !color ? (cull ? run_variant<false, false, false, false, true> : run_variant<false, false, false, false, false>)
-          : fast ? (cull ? run_variant<true, false, false, true, true> : run_variant<true, false, false, true, false>)
-                 : (cull ? run_variant<true, false, false, false, true> : run_variant<true, false, false, false, false>);
+    void (*entry)(void*) = !color ? run_direct<false, false, false, 3> : delta ? run_direct<true, false, true, 3> : run_direct<true, false, false, 3>;
+    emu::run_grid(dim3(std::max(ctas, 1)), dim3(INT_THREADS), entry, &ia);
   }
-  if (rev == 2) {      // integrate_kernel_r2: 128-thread CTAs with the staging buffers in dynamic shared memory, two steps at a time
-    const bool delta = S.weight_bound <= 65536u;
-    entry = !color ? (cull ? run_r2<false, false, false, true, 2> : run_r2<false, false, false, false, 2>)
-          : delta ? (cull ? run_r2<true, false, true, true, 2> : run_r2<true, false, true, false, 2>)
-                  : (cull ? run_r2<true, false, false, true, 2> : run_r2<true, false, false, false, 2>);
-    emu::run_grid(dim3(std::max(ctas, 1)), dim3(R2_THREADS), entry, &ia, integrate_r2_smem_bytes());
-    return;
-  }
-  emu::run_grid(dim3(std::max(ctas, 1)), dim3(INT_THREADS), entry, &ia);
 }
 
 }  // namespace vh
@@ -78,7 +67,7 @@ extern "C" {
 struct emu_integrate_io {
   int W, H;
   float fx, fy, cx, cy, max_depth, vox_size, trunc;
-  int use_color, cull, two_steps, verify, exact_color, ctas, variant;   // ctas: emulated grid size in 256-thread CTAs; variant: kernel revision (0 = shipped default)
+  int use_color, cull, two_steps, verify, exact_color, ctas, variant;   // ctas: emulated grid size in CTAs; variant: 1 = direct kernel, 2 = staged, 3 = direct with 64-bit voxel indices
   unsigned weight_bound, frame, rcp_seed;
   const float* c2w;              // [16]
   const float* depth;            // [H*W]
@@ -108,7 +97,8 @@ int emu_integrate(emu_integrate_io* io) {
   for (int i = 0; i < n; i++) { keys[i] = pack_key(io->keys_xyz[3 * i], io->keys_xyz[3 * i + 1], io->keys_xyz[3 * i + 2]); visible[i] = i; }
   const int tiles = ((io->W + 15) / 16) * ((io->H + 15) / 16);
   std::vector<float> tile_max(tiles, -1.0f);
-  std::vector<int> sched(NSCHED * 32, 12345);    // pack_frame_kernel must zero the counters it owns
+  std::vector<int> sched((NSCHED + 1) * 32, 12345);    // pack_frame_kernel must zero the counters it owns
+  std::vector<uint4> work(std::max(n, 1));
   std::vector<uint2> px((size_t)io->W * io->H + 1, make_uint2(0u, 0u));   // + the sentinel record (vh_create)
   FrameCounters counters; memset(&counters, 0xAB, sizeof(counters));
   int engine_error = 0; unsigned long long updates_total = 0;
@@ -121,36 +111,31 @@ int emu_integrate(emu_integrate_io* io) {
   DeviceView D; memset(&D, 0, sizeof(D));
   D.map.keys = keys.data(); D.map.slots = const_cast<int*>(io->slots);
   D.sdf = io->sdf; D.wgt = io->wgt; D.rgb = reinterpret_cast<uchar4*>(io->rgb4); D.neg_count = io->neg_count;
-  D.sched = sched.data(); D.tile_max = tile_max.data(); D.visible = visible.data(); D.list_cap = std::max(n, 1);
+  D.sched = sched.data(); D.work = work.data(); D.tile_max = tile_max.data(); D.visible = visible.data(); D.list_cap = std::max(n, 1);
   D.counters = &counters; D.engine_error = &engine_error; D.updates_total = &updates_total;
 
   IntegrateArgs ia{S, F, px.data(), D, 0};
-  const bool color = io->use_color != 0, fast = !io->exact_color && S.weight_bound <= 4096u;
+  const bool color = io->use_color != 0, delta = !io->exact_color && S.weight_bound <= 65536u;
   void (*entry)(void*) = nullptr;
-#define PICK(C, V, T, Q) (io->cull ? run_variant<C, V, T, Q, true> : run_variant<C, V, T, Q, false>)
-  if (io->verify) entry = !color ? PICK(false, true, false, false) : fast ? PICK(true, true, false, true) : PICK(true, true, false, false);
-  else if (io->two_steps) entry = !color ? PICK(false, false, true, false) : fast ? PICK(true, false, true, true) : PICK(true, false, true, false);
-  else entry = !color ? PICK(false, false, false, false) : fast ? PICK(true, false, false, true) : PICK(true, false, false, false);
-#undef PICK
-  if (io->variant == 1) {     // integrate_kernel_r1, dispatched like launch_integrate does
-    const bool delta = !io->exact_color && S.weight_bound <= 65536u;
-#define PICK1(C, V, DL) (io->cull ? run_r1<C, V, DL, true> : run_r1<C, V, DL, false>)
-    if (io->verify) entry = !color ? PICK1(false, true, false) : delta ? PICK1(true, true, true) : PICK1(true, true, false);
-    else entry = !color ? PICK1(false, false, false) : delta ? PICK1(true, false, true) : PICK1(true, false, false);
-#undef PICK1
-  }
   emu::g_collectives = 0;
-  if (io->variant == 2) {     // integrate_kernel_r2 (bulk-copy staging); two_steps selects the number of steps gated together
-    const bool delta = !io->exact_color && S.weight_bound <= 65536u;
-#define PICK2N(C, V, DL, NS) (io->cull ? run_r2<C, V, DL, true, NS> : run_r2<C, V, DL, false, NS>)
-#define PICK2(C, V, DL) (io->two_steps ? PICK2N(C, V, DL, 2) : PICK2N(C, V, DL, 1))
+  emu::run_grid(dim3(2), dim3(256), run_cull_list, &ia);
+  if (io->variant == 2) {     // integrate_kernel_staged; two_steps selects the number of steps gated together
+#define PICK2(C, V, DL) (io->two_steps ? run_staged<C, V, DL, 2> : run_staged<C, V, DL, 1>)
     if (io->verify) entry = !color ? PICK2(false, true, false) : delta ? PICK2(true, true, true) : PICK2(true, true, false);
     else entry = !color ? PICK2(false, false, false) : delta ? PICK2(true, false, true) : PICK2(true, false, false);
 #undef PICK2
-#undef PICK2N
-    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(R2_THREADS), entry, &ia, integrate_r2_smem_bytes());
-  } else
-  emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(INT_THREADS), entry, &ia);
+    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes());
+  } else if (io->variant == 3) {      // integrate_kernel_direct with 64-bit voxel indices
+    if (io->verify) entry = !color ? run_direct_wide<false, true, false> : delta ? run_direct_wide<true, true, true> : run_direct_wide<true, true, false>;
+    else entry = !color ? run_direct_wide<false, false, false> : delta ? run_direct_wide<true, false, true> : run_direct_wide<true, false, false>;
+    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(INT_THREADS), entry, &ia);
+  } else {                    // integrate_kernel_direct; two_steps selects the 4-CTA (64-register) build
+#define PICK1(C, V, DL) (io->two_steps ? run_direct<C, V, DL, 4> : run_direct<C, V, DL, 3>)
+    if (io->verify) entry = !color ? PICK1(false, true, false) : delta ? PICK1(true, true, true) : PICK1(true, true, false);
+    else entry = !color ? PICK1(false, false, false) : delta ? PICK1(true, false, true) : PICK1(true, false, false);
+#undef PICK1
+    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(INT_THREADS), entry, &ia);
+  }
   io->voxel_updates = counters.voxel_updates; io->culled = counters.pad[1]; io->mismatch = counters.pad[0];
   io->collectives = emu::g_collectives; io->slow_steps = counters.pad[2]; io->engine_error = engine_error;
   return updates_total == counters.voxel_updates ? 0 : -3;

@@ -52,8 +52,9 @@ def run_case(ob, synth, *, scene_kw, vox, trunc, maxd=3.0, frames=3, color=True,
 SMALL = dict(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=60, spheres=((2.8, 1.5, 1.0, 0.4),), color=True)
 
 
-# kernel revisions: 0 = integrate_kernel, 1 = integrate_kernel_r1, 2 = integrate_kernel_r2 (planes staged in shared memory by bulk copies)
-REVS = [0, 1, 2]
+# integrate kernels: 1 = integrate_kernel_direct (per-lane plane loads), 2 = integrate_kernel_staged (planes staged in shared memory by
+# bulk copies), 3 = the direct kernel with 64-bit voxel indices; all consume the work list of cull_list_kernel
+REVS = [1, 2, 3]
 
 
 @pytest.mark.parametrize("rev", REVS)
@@ -73,7 +74,7 @@ def test_emulated_integrate_fine_voxels_discards_blocks(ob, synth, rev):
     assert culled2 == 0 and upd2 == upd
 
 
-@pytest.mark.parametrize("kernel_kw", [dict(two_steps=1), dict(exact_color=1), dict(verify=1), dict(ctas=1),
+@pytest.mark.parametrize("kernel_kw", [dict(variant=1, two_steps=1), dict(variant=1, ctas=1),
                                        dict(variant=1, exact_color=1), dict(variant=1, verify=1), dict(variant=1, verify=1, exact_color=1),
                                        dict(variant=2, two_steps=1), dict(variant=2, exact_color=1), dict(variant=2, verify=1, two_steps=1), dict(variant=2, ctas=1)])
 def test_emulated_integrate_variants(ob, synth, kernel_kw):

@@ -8,8 +8,7 @@ import pytest
 from test_gpu_parity import assert_triangles_match, assert_voxels_match, run_pair
 from util import CASES, engine_params, key_set, load_golden, oracle_params
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VH_TEST_REV1") != "1", reason="opt-in kernel revision: set VH_TEST_REV1=1 (tools/gpu_rev1.sh)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(params=["0", "1"], ids=["integrate0", "integrate1"])

@@ -11,8 +11,7 @@ import pytest
 from test_gpu_parity import assert_triangles_match, assert_voxels_match
 from util import engine_params, key_set, oracle_params
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VH_TEST_REV1") != "1", reason="not yet run on a GPU: set VH_TEST_REV1=1 (tools/gpu_rev1.sh)")]
+pytestmark = pytest.mark.gpu
 
 
 def run_config(vh, ob, synth, name, frames, over, full_map=False, **eng):

@@ -9,8 +9,7 @@ import pytest
 from test_gpu_parity import assert_triangles_match, assert_voxels_match
 from util import engine_params, key_set, oracle_params
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VH_TEST_REV1") != "1", reason="not yet run on a GPU: set VH_TEST_REV1=1 (tools/gpu_rev1.sh)")]
+pytestmark = pytest.mark.gpu
 
 SMALL = dict(width=320, height=240, room=(9.0, 7.0, 2.6), n_frames=60, spheres=((6.9, 3.5, 1.0, 0.5),), color=True)
 CASE = dict(scene=dict(color=True), vpb=8, vox_size=0.02, trunc=0.1, max_depth=4.0)

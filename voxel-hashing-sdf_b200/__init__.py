@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "vh_extract_mesh", "vh_save_ply", "vh_save_ply_binary", "vh_weld_mesh", "vh_host_alloc", "vh_host_free",
     "vh_map_create", "vh_map_destroy", "vh_map_insert", "vh_map_find", "vh_map_erase", "vh_map_size", "vh_map_keys",
     "vh_map_get_view",
-    "vh_owner_of_block", "vh_shard_unique_id", "vh_shard_connect", "vh_integrate_sharded", "vh_shard_gather_mesh", "vh_shard_stats",
+    "vh_owner_of_block", "vh_shard_unique_id", "vh_shard_connect", "vh_integrate_sharded", "vh_integrate_sharded_device", "vh_shard_barrier", "vh_shard_gather_mesh", "vh_shard_stats",
     "vh_mesh_order_merge",
     "vh_far_blocks", "vh_blocks_resident", "vh_evict_blocks", "vh_upload_blocks",
 ]
@@ -65,7 +65,8 @@ class VhStats(C.Structure):
                 ("voxel_updates", C.c_uint64), ("voxel_updates_total", C.c_uint64),
                 ("triangles", C.c_uint64), ("arena_triangles", C.c_uint64),
                 ("ms_upload", C.c_float), ("ms_alloc", C.c_float), ("ms_integrate", C.c_float), ("ms_mc", C.c_float),
-                ("debug_mismatches", C.c_uint64), ("arena_compactions", C.c_uint64), ("forced_syncs", C.c_uint64), ("culled_blocks", C.c_uint64)]
+                ("debug_mismatches", C.c_uint64), ("arena_compactions", C.c_uint64), ("forced_syncs", C.c_uint64), ("culled_blocks", C.c_uint64),
+                ("ms_cull", C.c_float), ("reserved_f", C.c_float)]
 
 
 TRI_DTYPE = np.dtype([("xyz0", np.float32, 3), ("rgb0", np.uint8, 4), ("xyz1", np.float32, 3), ("rgb1", np.uint8, 4),
@@ -133,6 +134,8 @@ def load_library():
     L.vh_shard_unique_id.argtypes = [vp]
     L.vh_shard_connect.argtypes = [vp, vp]
     L.vh_integrate_sharded.argtypes = [vp, vp, vp, vp]
+    L.vh_integrate_sharded_device.argtypes = [vp, vp, vp, vp]
+    L.vh_shard_barrier.argtypes = [vp]
     L.vh_shard_gather_mesh.argtypes = [vp, ip, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.vh_shard_stats.argtypes = [vp, C.POINTER(VhStats)]
     L.vh_mesh_order_merge.argtypes = [ip, vp, vp, ip, vp, vp]
@@ -278,6 +281,15 @@ class TsdfEngine:
             c2w = np.ascontiguousarray(c2w, np.float32)
         self._keep = (depth, rgb, c2w)
         _check(self.L.vh_integrate_sharded(self.h, _ptr(depth), _ptr(rgb), _ptr(c2w)))
+
+    def integrate_sharded_device(self, d_depth, d_rgb, c2w):
+        """collective; device pointers (ints) of a frame resident in rank 0's HBM, None on ranks > 0"""
+        c2w = np.ascontiguousarray(c2w, np.float32)
+        self._keep = (c2w,)
+        _check(self.L.vh_integrate_sharded_device(self.h, d_depth, d_rgb, _ptr(c2w)))
+
+    def shard_barrier(self):
+        _check(self.L.vh_shard_barrier(self.h))
 
     def shard_triangles(self, mode=VH_MESH_REF_PERSISTENT):
         """collective; the merged soup on rank 0, empty arrays elsewhere"""

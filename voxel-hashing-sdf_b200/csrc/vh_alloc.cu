@@ -374,12 +374,257 @@ alloc_visible_kernel_r1(const StaticParams S, const FrameParams F, const float* 
     if (base + i < D.list_cap) D.visible[base + i] = s_first[i];
 }
 
+// ======================================================================================================================
+// Revision 2: allocation as TWO kernels with a key list in between — ray_keys_kernel -> (inbox) -> insert_keys_kernel.
+// The one-kernel forms above interleave a few thousand DDA steps with hash-table insertions inside every CTA: each round of
+// 256 keys walks a chain of dependent global accesses (probe -> CAS -> pool pop -> stamp exchange -> list append) with at most
+// 20 warps per SM to hide it (profiles/r02b: 24 us, issue slots 28 % busy, barrier + long-scoreboard stalls), and at the
+// 1,100-step cap of the room-scale config that chain repeats 34 times per CTA (0.40 ms). Split in two:
+//   ray_keys_kernel    the merge formulation of the DDA (see alloc_visible_kernel_r1) for a tile of TRX x TRY rays, then every key of
+//                      the tile is classified (ray end, chunk candidate test, frustum test) — pure arithmetic, no global access — and
+//                      the survivors are appended to the INBOX of the GPU that owns the block: one reservation per owner per CTA.
+//                      On a single GPU the owner is this GPU; on a sharded map the inbox of a peer is written over NVLink (stores
+//                      into its mapped memory), and each GPU marches only every shard_count-th tile of rays: the ray pass is SPLIT
+//                      across the GPUs, not replicated.
+//   insert_keys_kernel one thread per inbox key, as many CTAs as the GPU holds: claim (64-bit CAS), pool pop and key_heap append
+//                      aggregated per CTA (ONE atomicSub + ONE atomicAdd per 512 keys: at ~1 M new blocks per frame per-warp atomics
+//                      on the two counters would serialise in L2), stamp exchange, first-seen entries appended to the visible list
+//                      with one atomicAdd per CTA.
+// Between the two a sharded map needs every peer's keys to have arrived: the frame barrier of vh_shard.cu. The inbox is
+// double-buffered by frame parity (a peer may already be writing frame f+1 while this GPU inserts frame f).
+template <int TRX, int TRY>
+__device__ __forceinline__ void merge_fill_keys_t(const StaticParams& S, const FrameParams& F, const float* __restrict__ depth, int tile_x, int tile_y,
+                                                  u64* __restrict__ skeys, float* __restrict__ sT, int* __restrict__ s_death) {
+  constexpr int NR = TRX * TRY;
+  __shared__ int s_cur[NR][3], s_step[NR][3], s_last[NR][3], s_alive[NR];
+  __shared__ float s_del[NR][3], s_inv[NR][3];
+  const int K = S.max_steps;
+  const int tid = threadIdx.x, nthreads = (int)blockDim.x;
+
+  // phase 0: ray set-up (one lane per ray), every step slot empty
+  if (tid < NR) {
+    RayState R;
+    ray_setup(S, F, depth, tile_x * TRX + (tid % TRX), tile_y * TRY + (tid / TRX), R);
+    s_alive[tid] = R.alive ? 1 : 0;
+    s_death[tid] = K;                                                 // no step ends the ray (yet)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      s_cur[tid][a] = R.cur[a]; s_step[tid][a] = R.istep[a];
+      // the a-step that carries cur_a onto bound_a is number (bound - cur) / step, counted from 1; none if the bound is not ahead
+      const long long ahead = ((long long)R.bound[a] - (long long)R.cur[a]) * (long long)R.istep[a];
+      s_last[tid][a] = (R.istep[a] != 0 && ahead >= 1 && ahead <= (long long)K) ? (int)ahead - 1 : -1;
+      sT[(tid * 3 + a) * K] = R.tmax[a];
+      s_del[tid][a] = R.tdel[a];
+      s_inv[tid][a] = R.tdel[a] > 0.0f ? fdiv(1.0f, R.tdel[a]) : 0.0f;         // estimate only (merge_rank_near); +inf -> 0
+    }
+  }
+  for (int i = tid; i < K * NR; i += nthreads) skeys[i] = KEY_EMPTY;
+  __syncthreads();
+
+  // phase 1: the crossing times of every axis by repeated addition (tsdf.cu:2221,2226,2231), one lane per (ray, axis)
+  if (tid < NR * 3) {
+    float* t = sT + (size_t)tid * K;
+    float v = t[0];
+    const float del = s_del[tid / 3][tid % 3];
+    for (int k = 1; k < K; k++) { v = fadd(v, del); t[k] = v; }
+  }
+  __syncthreads();
+
+  // phase 2: every element finds its step and the block the ray is in when it takes it: items (ray, axis, k) flattened over the CTA
+  for (int i = tid; i < NR * 3 * K; i += nthreads) {
+    const int ra = i / K, k = i - ra * K;
+    const int ray = ra / 3, a = ra - ray * 3;
+    if (!s_alive[ray]) continue;
+    const int b = a == 0 ? 1 : 0, c = a == 2 ? 1 : 2;                 // the other two axes
+    const int pa = axis_priority(a);
+    const bool tb = axis_priority(b) < pa, tc = axis_priority(c) < pa;
+    const float* Tb = sT + (size_t)(ray * 3 + b) * K;
+    const float* Tc = sT + (size_t)(ray * 3 + c) * K;
+    const float v = sT[(size_t)ra * K + k];
+    const int nb = merge_rank_near(Tb, K, v, tb, s_inv[ray][b]);
+    if (k + nb >= K) continue;
+    const int nc = merge_rank_near(Tc, K, v, tc, s_inv[ray][c]);
+    const int pos = k + nb + nc;
+    if (pos < 0 || pos >= K) continue;
+    int cur[3];
+    cur[a] = s_cur[ray][a] + k * s_step[ray][a]; cur[b] = s_cur[ray][b] + nb * s_step[ray][b]; cur[c] = s_cur[ray][c] + nc * s_step[ray][c];
+    if (key_in_range(cur[0], cur[1], cur[2])) skeys[pos * NR + ray] = pack_key(cur[0], cur[1], cur[2]);
+    if (k == s_last[ray][a]) atomicMin(&s_death[ray], pos);           // this step moves the ray onto its bound (tsdf.cu:2219,2224,2229)
+  }
+  __syncthreads();
+}
+
+constexpr int KEYS_THREADS = 256;
+template <int TRX, int TRY>
+__global__ void __launch_bounds__(KEYS_THREADS)
+ray_keys_kernel(const __grid_constant__ StaticParams S, const __grid_constant__ FrameParams F, const float* __restrict__ depth, const __grid_constant__ DeviceView D,
+                int tiles_x, int n_tiles) {
+  constexpr int NR = TRX * TRY;
+#ifdef VH_HOST_EMU
+  u64* dyn = reinterpret_cast<u64*>(emu::g_cta->dyn_smem);
+#else
+  extern __shared__ u64 dyn[];
+#endif
+  const int K = S.max_steps;
+  u64* skeys = dyn;                                                   // [K][NR]
+  float* sT = reinterpret_cast<float*>(dyn + (size_t)K * NR);         // [NR][3][K] crossing times (dead after phase 2)
+  __shared__ int s_death[NR];
+  __shared__ int s_cnt[MAX_SHARDS], s_base[MAX_SHARDS], s_fill[MAX_SHARDS];
+  const int tid = threadIdx.x;
+  // a connected sharded map splits the tiles of rays across its GPUs (keys travel to their owner's inbox); a shard without
+  // peers marches every tile and keeps its own keys
+  const bool routed = S.shard_count > 1 && D.peers != nullptr;
+  const int tile = routed ? (int)blockIdx.x * (int)S.shard_count + (int)S.shard_rank : (int)blockIdx.x;
+  if (tile >= n_tiles) return;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  if (tid < MAX_SHARDS) { s_cnt[tid] = 0; s_fill[tid] = 0; }
+  merge_fill_keys_t<TRX, TRY>(S, F, depth, tile_x, tile_y, skeys, sT, s_death);
+
+  // classify every key of the tile; the survivors stay in skeys (the rest become KEY_EMPTY) and are counted per owner
+  const float bpc = (float)S.bpc;
+  const int nkeys = K * NR;
+  const int parity = (int)(F.frame & 1u);
+  for (int i = tid; i < nkeys; i += KEYS_THREADS) {
+    u64 key = skeys[i];
+    if (key == KEY_EMPTY) continue;
+    bool ok = i / NR <= s_death[i % NR];
+    int owner = 0;
+    if (ok) {
+      int bx, by, bz;
+      unpack_key(key, bx, by, bz);
+      ok = chunk_is_candidate(S, F, block_to_chunk(bx, bpc), block_to_chunk(by, bpc), block_to_chunk(bz, bpc));   // tsdf.cu:2164
+      if (ok) ok = block_in_frustum(S, F, bx, by, bz);                                                          // tsdf.cu:2165
+      if (ok && S.shard_count > 1) {
+        owner = (int)owner_of_block(bx, by, bz, S.shard_count, S.shard_group);
+        if (!routed) { ok = owner == (int)S.shard_rank; owner = 0; }
+      }
+    }
+    if (ok) atomicAdd(&s_cnt[owner], 1); else skeys[i] = KEY_EMPTY;
+  }
+  __syncthreads();
+  // one reservation per owner per CTA, in the owner's inbox (a peer's: a remote atomic over NVLink)
+  if (tid < MAX_SHARDS && s_cnt[tid] > 0) {
+    int* cnt = routed ? D.peers->v[tid].inbox_count : D.inbox_count;
+    s_base[tid] = atomicAdd(&cnt[parity], s_cnt[tid]);
+  }
+  __syncthreads();
+  for (int i = tid; i < nkeys; i += KEYS_THREADS) {
+    const u64 key = skeys[i];
+    if (key == KEY_EMPTY) continue;
+    int owner = 0;
+    if (routed) { int bx, by, bz; unpack_key(key, bx, by, bz); owner = (int)owner_of_block(bx, by, bz, S.shard_count, S.shard_group); }
+    const int pos = s_base[owner] + atomicAdd(&s_fill[owner], 1);
+    u64* box = routed ? D.peers->v[owner].inbox : D.inbox;
+    if (pos < D.inbox_cap) box[(size_t)parity * D.inbox_cap + pos] = key;
+    else atomicOr(D.map.error_flag, MAP_TABLE_FULL);
+  }
+}
+
+inline size_t ray_keys_smem_bytes(int max_steps, int rays) {
+  return (size_t)max_steps * rays * sizeof(u64) + (size_t)rays * 3 * max_steps * sizeof(float);     // keys + crossing times (20 B per ray-step)
+}
+
+constexpr int INSERT_THREADS = 512;
+__global__ void __launch_bounds__(INSERT_THREADS)
+insert_keys_kernel(const __grid_constant__ DeviceView D, const uint32_t frame) {
+  __shared__ int s_wclaim[INSERT_THREADS / 32], s_wfirst[INSERT_THREADS / 32];
+  __shared__ int s_top, s_heap, s_vis;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int parity = (int)(frame & 1u);
+  const int n = min(D.inbox_count[parity], D.inbox_cap);
+  const u64* box = D.inbox + (size_t)parity * D.inbox_cap;
+  for (int base = (int)blockIdx.x * INSERT_THREADS; base < n; base += (int)gridDim.x * INSERT_THREADS) {
+    const int i = base + tid;
+    const u64 key = i < n ? box[i] : KEY_EMPTY;
+    int entry = -1;
+    bool claimed = false;
+    if (key != KEY_EMPTY) entry = map_claim(D.map, key, claimed);
+    bool first = false;
+    if (entry >= 0) first = atomicExch(&D.stamps[entry], frame) != frame;     // exactly one thread per block and frame
+    const unsigned cm = __ballot_sync(0xffffffffu, claimed), fm = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) { s_wclaim[wid] = __popc(cm); s_wfirst[wid] = __popc(fm); }
+    __syncthreads();
+    if (wid == 0) {     // exclusive scan of the per-warp counts; ONE pop, ONE key_heap reservation, ONE visible-list reservation per CTA
+      const int c = lane < INSERT_THREADS / 32 ? s_wclaim[lane] : 0, f = lane < INSERT_THREADS / 32 ? s_wfirst[lane] : 0;
+      int ci = c, fi = f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ci, o), v = __shfl_up_sync(0xffffffffu, fi, o); if (lane >= o) { ci += u; fi += v; } }
+      if (lane < INSERT_THREADS / 32) { s_wclaim[lane] = ci - c; s_wfirst[lane] = fi - f; }
+      const int nc = __shfl_sync(0xffffffffu, ci, 31), nf = __shfl_sync(0xffffffffu, fi, 31);
+      if (lane == 0) {
+        int top = 0, heap = 0, vis = 0;
+        if (nc > 0) {
+          top = atomicSub(D.map.free_top, nc);
+          const int granted = top >= nc ? nc : (top > 0 ? top : 0);
+          if (granted < nc) atomicAdd(D.map.free_top, nc - granted);          // pool exhausted: hand back the share that was not there
+          if (granted > 0) heap = atomicAdd(D.map.heap_counter, granted);
+        }
+        if (nf > 0) vis = atomicAdd(&D.counters->visible_count, nf);
+        s_top = top; s_heap = heap; s_vis = vis;
+      }
+    }
+    __syncthreads();
+    if (claimed) {
+      const int rank = s_wclaim[wid] + __popc(cm & ((1u << lane) - 1));
+      const int idx = s_top - 1 - rank;
+      if (idx >= 0) {
+        D.map.slots[entry] = D.map.free_list[idx];
+        if (s_heap + rank < D.map.num_blocks) D.map.key_heap[s_heap + rank] = key;
+      } else {
+        D.map.slots[entry] = SLOT_POOL_FULL;
+        atomicOr(D.map.error_flag, MAP_POOL_FULL);
+      }
+    }
+    if (first) {
+      const int pos = s_vis + s_wfirst[wid] + __popc(fm & ((1u << lane) - 1));
+      if (pos < D.list_cap) D.visible[pos] = entry;
+    }
+    __syncthreads();                 // the shared counters are rewritten in the next round
+  }
+  // The last CTA to finish empties the inbox of this parity for frame + 2 (every CTA read the count before it got here; a
+  // peer writes this parity again only after the next frame's barrier, which this GPU reaches after this kernel).
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&D.inbox_done[parity], 1) == (int)gridDim.x - 1) { D.inbox_count[parity] = 0; D.inbox_done[parity] = 0; __threadfence(); }
+  }
+}
+
 inline size_t alloc_r1_smem_bytes(int max_steps) {
   return (size_t)max_steps * RAYS * sizeof(u64) + (size_t)RAYS * 3 * max_steps * sizeof(float);     // keys + crossing times (160 B per step)
 }
 
 #ifndef VH_HOST_EMU
+// first half of the allocation: the frame's block keys into their owners' inboxes (revision 2)
+template <int TRX, int TRY>
+static void launch_ray_keys_t(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st) {
+  const int tiles_x = (S.nrx + TRX - 1) / TRX, tiles_y = (S.nry + TRY - 1) / TRY, n_tiles = tiles_x * tiles_y;
+  const bool routed = S.shard_count > 1 && D.peers != nullptr;
+  const int grid = routed ? (n_tiles + (int)S.shard_count - 1) / (int)S.shard_count : n_tiles;
+  const size_t smem = ray_keys_smem_bytes(S.max_steps, TRX * TRY);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(ray_keys_kernel<TRX, TRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ray_keys_kernel<TRX, TRY><<<grid, KEYS_THREADS, smem, st>>>(S, F, d_depth, D, tiles_x, n_tiles);
+}
+bool alloc_uses_inbox(const StaticParams& S) { return S.alloc_rev == 2 && ray_keys_smem_bytes(S.max_steps, 2) <= (size_t)ALLOC1_MAX_SMEM; }
+void launch_ray_keys(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, int num_sms, cudaStream_t st) {
+  // the largest tile of rays that still gives every SM a few CTAs (a sharded map marches 1/shard_count of the tiles per GPU)
+  const int rays = S.nrx * S.nry, share = (S.shard_count > 1 && D.peers) ? (int)S.shard_count : 1;
+  if (rays / 8 / share >= 4 * num_sms && ray_keys_smem_bytes(S.max_steps, 8) <= 64 * 1024) launch_ray_keys_t<4, 2>(S, F, d_depth, D, st);
+  else if (rays / 4 / share >= 4 * num_sms && ray_keys_smem_bytes(S.max_steps, 4) <= 96 * 1024) launch_ray_keys_t<2, 2>(S, F, d_depth, D, st);
+  else launch_ray_keys_t<2, 1>(S, F, d_depth, D, st);
+}
+// second half: this GPU's inbox into its table, pool and visible list
+void launch_insert_keys(const StaticParams& S, const FrameParams& F, const DeviceView& D, int num_sms, cudaStream_t st) {
+  insert_keys_kernel<<<num_sms * 3, INSERT_THREADS, 0, st>>>(D, F.frame);
+}
+
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st) {
+  if (alloc_uses_inbox(S)) {      // a connected sharded map needs its frame barrier between the two: vh_shard.cu launches them itself
+    int dev = 0, num_sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    launch_ray_keys(S, F, d_depth, D, num_sms, st);
+    launch_insert_keys(S, F, D, num_sms, st);
+    return;
+  }
   const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;
   if (S.alloc_rev == 1 && alloc_r1_smem_bytes(S.max_steps) <= (size_t)ALLOC1_MAX_SMEM) {      // opt-in revision, see alloc_visible_kernel_r1
     const size_t smem1 = alloc_r1_smem_bytes(S.max_steps);

@@ -71,7 +71,7 @@ static int free_engine(vh_engine* e) {
   if (e->upload) cudaStreamSynchronize(e->upload);
   DeviceView& D = e->D;
   cudaFree(D.map.keys); cudaFree(D.map.slots); cudaFree(D.map.free_list); cudaFree(D.map.free_top); cudaFree(D.map.key_heap);
-  cudaFree(e->d_status); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.tile_max); cudaFree(D.sched); cudaFree(D.neg_count); cudaFree(D.mc_queue); cudaFree(D.mc_ctl); cudaFree(D.visible);
+  cudaFree(e->d_status); cudaFree(D.stamps); cudaFree(D.sdf); cudaFree(D.wgt); cudaFree(D.rgb); cudaFree(D.tile_max); cudaFree(D.sched); cudaFree(D.work); cudaFree(D.neg_count); cudaFree(D.mc_queue); cudaFree(D.mc_ctl); cudaFree(D.visible); cudaFree(D.inbox); cudaFree(D.inbox_count);
   cudaFree(D.arena); cudaFree(e->arena_spare); cudaFree(e->d_scan_in); cudaFree(e->d_scan_out); cudaFree(e->d_scan_tmp);
   cudaFree(D.tri_offset); cudaFree(D.tri_count);
   cudaFree(e->d_full_list); cudaFree(e->d_full_count); cudaFree(e->d_full_off); cudaFree(e->d_full_cnt); cudaFree(e->d_keys_tmp);
@@ -81,7 +81,7 @@ static int free_engine(vh_engine* e) {
     if (e->ev_rgb[i]) cudaEventDestroy(e->ev_rgb[i]);
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
   }
-  for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->ev_mapped_read) cudaEventDestroy(e->ev_mapped_read);
   if (e->h_block) cudaFreeHost(e->h_block);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -107,6 +107,7 @@ static int reset_map(vh_engine* e) {
   if (D.rgb) CK(cudaMemsetAsync(D.rgb, 0, (size_t)nb * BLOCK_VOX * sizeof(uchar4), e->stream));
   CK(cudaMemsetAsync(D.neg_count, 0, (size_t)nb * sizeof(int), e->stream));
   CK(cudaMemsetAsync(D.mc_ctl, 0, 2 * sizeof(McQueueCtl), e->stream));
+  CK(cudaMemsetAsync(D.inbox_count, 0, 4 * sizeof(int), e->stream));
   CK(cudaMemsetAsync(D.tri_offset, 0, (size_t)nb * sizeof(unsigned long long), e->stream));
   CK(cudaMemsetAsync(D.tri_count, 0, (size_t)nb * sizeof(int), e->stream));
   CK(cudaMemsetAsync(e->d_status, 0, sizeof(DeviceStatus), e->stream));
@@ -143,13 +144,13 @@ int vh_create(const vh_params* p, vh_engine** out) {
   StaticParams& S = e->S;
   derive_static_params(*p, S);
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
-  { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && ((v[0] >= '2' && v[0] <= '4') || v[0] == '7')) ? v[0] - '0' : 4; }   // tuning knobs (7: revision 1 only, 7 CTAs of 128 threads)
+  { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && (v[0] == '3' || v[0] == '4')) ? v[0] - '0' : 0; }   // tuning knob; 0 = the kernel's default (direct 3, staged 4)
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_env = e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
-  { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '1') ? 1 : 0; }
-  { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 0; }
-  { const char* v = getenv("VH_ALLOC_REV"); S.alloc_rev = (v && v[0] == '1') ? 1 : 0; }
-  { const char* v = getenv("VH_MC_REV"); S.mc_rev = (v && v[0] == '1') ? 1 : 0; }
+  { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '0') ? 0 : 1; }
+  { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] == '1') ? 1 : 2; }      // 2 (default) = integrate_kernel_staged, 1 = integrate_kernel_direct
+  { const char* v = getenv("VH_ALLOC_REV"); S.alloc_rev = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 0; }
+  S.mc_rev = 0;      // (unused: the marching-cubes revisions of round 1 were measured and merged)
   static_assert(sizeof(StaticParams) % 16 == 0, "keep the FrameParams behind StaticParams 16-byte aligned in the kernels' parameter blocks");
 
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket;
@@ -181,11 +182,16 @@ int vh_create(const vh_params* p, vh_engine** out) {
   ALLOC(D.wgt, nb * BLOCK_VOX * sizeof(float));
   if (S.use_color) ALLOC(D.rgb, nb * BLOCK_VOX * sizeof(uchar4));
   ALLOC(D.neg_count, nb * sizeof(int));
-  ALLOC(D.sched, 8 * 32 * sizeof(int));
+  ALLOC(D.sched, 9 * 32 * sizeof(int));
+  ALLOC(D.work, (size_t)D.list_cap * sizeof(uint4));
   ALLOC(D.tile_max, (size_t)((p->width + 15) / 16) * ((p->height + 15) / 16) * sizeof(float));
   ALLOC(D.mc_queue, (size_t)D.list_cap * sizeof(McWork));
   ALLOC(D.mc_ctl, 2 * sizeof(McQueueCtl));
   ALLOC(D.visible, (size_t)D.list_cap * sizeof(int));
+  D.inbox_cap = (int)std::max<size_t>(rays * (size_t)S.max_steps, 1024);
+  ALLOC(D.inbox, 2 * (size_t)D.inbox_cap * sizeof(u64));
+  ALLOC(D.inbox_count, 4 * sizeof(int));
+  D.inbox_done = D.inbox_count + 2;
   ALLOC(D.arena, D.arena_cap * sizeof(vh_triangle));
   if (p->mc_per_frame) ALLOC(e->arena_spare, D.arena_cap * sizeof(vh_triangle));      // compaction target; the two swap roles
   ALLOC(D.tri_offset, nb * sizeof(unsigned long long));
@@ -215,13 +221,13 @@ int vh_create(const vh_params* p, vh_engine** out) {
     ok = cudaEventCreateWithFlags(&e->ev_uploaded[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_rgb[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
+  for (int i = 0; i < 6 && ok; i++) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&e->ev_mapped_read, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { free_engine(e); return fail(VH_ERR_CUDA, "CUDA Error: stream/event creation failed"); }
-  {   // tuning knob, off by default: publish the status block from a kernel instead of a D2H copy (see publish_status_kernel)
+  {   // the status block is published by a kernel into mapped pinned memory (see publish_status_kernel); VH_STATUS_PUBLISH=0 = D2H copy node instead
     const char* v = getenv("VH_STATUS_PUBLISH");
     void* dp = nullptr;
-    if (v && v[0] == '1') { if (cudaHostGetDevicePointer(&dp, e->h_block, 0) == cudaSuccess) e->h_block_dev = static_cast<DeviceStatus*>(dp); else cudaGetLastError(); }
+    if (!(v && v[0] == '0')) { if (cudaHostGetDevicePointer(&dp, e->h_block, 0) == cudaSuccess) e->h_block_dev = static_cast<DeviceStatus*>(dp); else cudaGetLastError(); }
   }
   upload_mc_tables();
   int rc = reset_map(e);
@@ -237,6 +243,7 @@ int vh_reset(vh_engine* e) {
   if (!e) return fail(VH_ERR_INVALID, "null engine");
   std::lock_guard<std::mutex> lk(e->mtx);
   CK(cudaSetDevice(e->P.device));
+  if (e->shard) { int rc = shard_barrier(e); if (rc != VH_OK) return rc; }     // sharded map (collective): no peer is still meshing against these voxels
   CK(cudaStreamSynchronize(e->stream));
   return reset_map(e);
 }
@@ -325,6 +332,8 @@ int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEve
     launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, do_alloc ? D.counters : nullptr, e->F.frame, e->stream);
     if (do_alloc) launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
   }
+  CK(cudaEventRecord(e->ev[5], e->stream));
+  launch_cull_list(e->S, e->F, D, e->num_sms, e->stream);          // integrate's work list: visible blocks minus the whole-block discards
   CK(cudaEventRecord(e->ev[2], e->stream));
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
@@ -335,7 +344,7 @@ int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEve
   return VH_OK;
 }
 
-// Experimental route of the status block (VH_STATUS_PUBLISH=1, off by default): one warp stores
+// The status block at the end of a frame (VH_STATUS_PUBLISH=0 falls back to a D2H copy node): one warp stores
 // the 128-byte block into the mapped pinned host block instead of a D2H copy node, so that the frame ends without a
 // kernel -> copy engine -> kernel hand-off and never queues behind the next frame's upload. Word 0 holds the frame stamp
 // the host polls without a sync (make_room); it is stored last, after a system-scope fence.
@@ -576,6 +585,7 @@ int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb)
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
   launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, e->D.tile_max, e->D.sched, nullptr, e->F.frame, e->stream);
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
+  launch_cull_list(e->S, e->F, e->D, e->num_sms, e->stream);
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, e->D, e->num_sms, e->stream);
   e->S.use_color = keep;
   int rc = enqueue_readback(e);
@@ -654,7 +664,8 @@ int vh_get_stats(vh_engine* e, vh_stats* out) {
   if (e->frames > 0) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) out->ms_upload = ms;
-    if (cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]) == cudaSuccess) out->ms_alloc = ms;
+    if (cudaEventElapsedTime(&ms, e->ev[1], e->ev[5]) == cudaSuccess) out->ms_alloc = ms;
+    if (cudaEventElapsedTime(&ms, e->ev[5], e->ev[2]) == cudaSuccess) out->ms_cull = ms;
     if (cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]) == cudaSuccess) out->ms_integrate = ms;
     if (cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]) == cudaSuccess) out->ms_mc = ms;
     cudaGetLastError();

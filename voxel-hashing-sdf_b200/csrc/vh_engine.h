@@ -38,11 +38,11 @@ struct StaticParams {
   int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
   uint32_t weight_bound;          // upper bound of any voxel weight after the coming integrate launch (= launches since reset)
   int integrate_cull;             // 1 (default): discard whole blocks behind everything seen in their footprint; 0: gate every voxel
-  int integrate_two_steps;        // tuning: 1 = gate/load/update two steps of a block together, 0 = one step at a time (default)
-  int integrate_ctas_per_sm;      // resident 256-thread CTAs per SM the integrate kernel is compiled for (2, 3 or 4; default 4)
+  int integrate_two_steps;        // staged kernel: 1 = gate two steps of a block together (8 pixel gathers in flight per lane), 0 = one step at a time
+  int integrate_ctas_per_sm;      // resident CTAs per SM the integrate kernel is compiled for (3 or 4; 0 = the kernel's default)
   uint32_t byte_bias;             // 0x4B000000 (bits of 2^23), read from the parameter block by integrate_kernel_r1's byte -> float permutes
-  int integrate_rev;              // 0 (default): integrate_kernel; 1: integrate_kernel_r1 (VH_INTEGRATE_REV=1, same results, fewer instructions)
-  int alloc_rev;                  // 0 (default): alloc_visible_kernel; 1: alloc_visible_kernel_r1 (VH_ALLOC_REV=1, same visible sets, no sequential DDA)
+  int integrate_rev;              // 1: integrate_kernel_direct; 2: integrate_kernel_staged (planes through shared memory by bulk async copies)
+  int alloc_rev;                  // 0: alloc_visible_kernel; 1: alloc_visible_kernel_r1 (merge formulation of the DDA); 2: ray_keys_kernel + insert_keys_kernel
   int mc_rev;                     // 0 (default); 1: the mesh kernel's emit pass issues a triangle's six colour gathers before interpolating (VH_MC_REV=1)
   // sizeof(StaticParams) stays a multiple of 16: the FrameParams that follows it in every kernel's parameter block keeps its
   // 16-byte alignment, so its pose is still fetched with 128-bit constant loads (add fields four ints at a time)
@@ -83,6 +83,7 @@ struct DeviceStatus {
 constexpr int MAX_SHARDS = 8;
 struct PeerView {
   const u64* keys; const int* slots; const uint32_t* stamps; const int* neg_count; const float* sdf; const uchar4* rgb;
+  u64* inbox; int* inbox_count;   // the shard's key inbox [2][inbox_cap] and its two fill counters (written by every peer's ray_keys_kernel)
   uint32_t mask; uint32_t pad;
 };
 struct PeerTable { PeerView v[MAX_SHARDS]; };
@@ -103,11 +104,16 @@ struct DeviceView {
   float* sdf;
   float* wgt;
   uchar4* rgb;
-  int* sched;                     // [8 * 32] work counters of the integrate kernel's block scheduler (zeroed by pack_frame_kernel)
+  int* sched;                     // [9 * 32] work counters of the integrate kernel's block scheduler + [8 * 32] = length of its work list (zeroed by pack_frame_kernel)
+  uint4* work;                    // [list_cap] integrate work list {key lo, key hi, slot, position in `visible`}: visible blocks that survive the whole-block discard
   float* tile_max;                // [ceil(H/16) * ceil(W/16)] maximum depth per 16x16-pixel tile of the current frame
   int* neg_count;                 // [pool_blocks] number of voxels with sdf < 0 per block, kept current by integrate_kernel
   int* visible;
   int list_cap;
+  u64* inbox;                     // [2][inbox_cap] block keys of the frame awaiting insertion, double-buffered by frame parity (ray_keys_kernel -> insert_keys_kernel)
+  int* inbox_count;               // [2] keys in each half; [2..3] = CTAs of insert_keys_kernel that have finished (the last one empties the half)
+  int* inbox_done;
+  int inbox_cap;
   FrameCounters* counters;
   // triangle store
   vh_triangle* arena;
@@ -126,8 +132,12 @@ struct DeviceView {
 
 // kernels (defined in the .cu files)
 void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, cudaStream_t st);
+bool alloc_uses_inbox(const StaticParams& S);
+void launch_ray_keys(const StaticParams& S, const FrameParams& F, const float* d_depth, const DeviceView& D, int num_sms, cudaStream_t st);
+void launch_insert_keys(const StaticParams& S, const FrameParams& F, const DeviceView& D, int num_sms, cudaStream_t st);
 void launch_pack_frame(const StaticParams& S, const float* d_depth, const uint8_t* d_rgb, uint2* d_out, float* d_tile_max, int* d_sched,
                        FrameCounters* reset_counters, uint32_t frame, cudaStream_t st, int stamp_only = 0);
+void launch_cull_list(const StaticParams& S, const FrameParams& F, const DeviceView& D, int num_sms, cudaStream_t st);
 void launch_integrate(const StaticParams& S, const FrameParams& F, const uint2* d_frame_px, bool color, const DeviceView& D, int num_sms,
                       cudaStream_t st);
 void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const DeviceView& D, const int* list, const int* list_count,

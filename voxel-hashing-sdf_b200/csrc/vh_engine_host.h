@@ -40,7 +40,7 @@ struct vh_engine {
   int ring = 0;
   const float* cur_depth = nullptr;     // device pointers the stage calls operate on
   const uint8_t* cur_rgb = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // frame start, inputs ready, integrate start, integrate end, frame end, work-list start
   // pinned read-back block: counters of the last frame + flags
   typedef DeviceStatus HostBlock;
   HostBlock* h_block = nullptr;
@@ -75,6 +75,7 @@ struct MeshBlocks {
 
 void setup_frame(vh_engine* e, const float* c2w);
 void shard_release(vh_engine* e);               // vh_shard.cu: called by vh_destroy
+int shard_barrier(vh_engine* e);                // vh_shard.cu: stream-ordered barrier across the GPUs of a sharded map (enqueue only)
 int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out, unsigned long long total, vh_triangle** d_keep);   // ordered soup of mb's blocks
 int weld_on_device(vh_engine* e, const vh_triangle* d_soup, unsigned long long T, std::vector<vh_vertex>& verts, std::vector<int32_t>& faces);   // vh_weld.cu
 extern "C" {

@@ -99,33 +99,10 @@ struct McBlock {            // per-warp context of the block being meshed
   int bx, by, bz;
 };
 
-// vertex on cube edge e of the voxel at tile position (lx,ly,lz)
-template <bool SHARDED>
-__device__ __forceinline__ Vtx edge_vertex(const McBlock& B, const DeviceView& D, int lx, int ly, int lz, int e, bool color) {
-  const int a = e < 8 ? e : e - 8;
-  const int b = e < 4 ? ((e + 1) & 3) : (e < 8 ? 4 + ((e - 3) & 3) : e - 4);
-  const int ax = lx + corner_ox(a), ay = ly + corner_oy(a), az = lz + corner_oz(a);
-  const int qx = lx + corner_ox(b), qy = ly + corner_oy(b), qz = lz + corner_oz(b);
-  Vtx pa, pb;
-  pa.x = i2f(B.bx * VPB + ax); pa.y = i2f(B.by * VPB + ay); pa.z = i2f(B.bz * VPB + az);      // Vertex(cxi, cyi, czi), tsdf.cu:931
-  pb.x = i2f(B.bx * VPB + qx); pb.y = i2f(B.by * VPB + qy); pb.z = i2f(B.bz * VPB + qz);
-  pa.c = 0; pb.c = 0;
-  if (color) {
-    const int ma = (ax >> 3) | ((ay >> 3) << 1) | ((az >> 3) << 2), mb = (qx >> 3) | ((qy >> 3) << 1) | ((qz >> 3) << 2);
-    const int sa = B.nb_slot[ma], sb = B.nb_slot[mb];
-    const uchar4* rgb_a = SHARDED ? D.peers->v[B.nb_owner[ma]].rgb : D.rgb;
-    const uchar4* rgb_b = SHARDED ? D.peers->v[B.nb_owner[mb]].rgb : D.rgb;
-    const uchar4 ca = rgb_a[(size_t)sa * BLOCK_VOX + ((ax & 7) * 64 + (ay & 7) * 8 + (az & 7))];
-    const uchar4 cb = rgb_b[(size_t)sb * BLOCK_VOX + ((qx & 7) * 64 + (qy & 7) * 8 + (qz & 7))];
-    pa.c = (uint32_t)ca.x | ((uint32_t)ca.y << 8) | ((uint32_t)ca.z << 16);
-    pb.c = (uint32_t)cb.x | ((uint32_t)cb.y << 8) | ((uint32_t)cb.z << 16);
-  }
-  return vertex_interp(pa, pb, B.tile[(ax * TILE + ay) * TILE + az], B.tile[(qx * TILE + qy) * TILE + qz], color);
-}
-
-// Revision 1 of the emit pass (opt-in: VH_MC_REV=1) splits edge_vertex in two so that the six colour gathers of a triangle
-// are all in flight before the first interpolation consumes one (the mesh kernel's stall samples sit on the unpacking of
-// a colour loaded two instructions earlier, one vertex at a time). Same operations, same results.
+// The vertex on cube edge e of the voxel at tile position (lx,ly,lz), in two halves: edge_fetch (addresses, the two sdf values,
+// the two colour gathers) and edge_finish (positions, VertexInterp). A triangle's three fetches are issued before the first
+// finish, so its six colour gathers are all in flight before the first interpolation consumes one (measured on B200 against
+// fetch-and-interpolate one vertex at a time: 0.069 -> 0.066 ms per frame, profiles/r02a).
 struct EdgeFetch { int a_pos, b_pos; float va, vb; uint32_t ca, cb; };   // positions packed x | y << 8 | z << 16 (tile coordinates 0..8)
 template <bool SHARDED>
 __device__ __forceinline__ EdgeFetch edge_fetch(const McBlock& B, const DeviceView& D, int lx, int ly, int lz, int e, bool color) {
@@ -167,14 +144,9 @@ __device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int
 
 // Mesh one block with the whole warp: stage the 9^3 tile, pass 1 lists candidate triangles, pass 2 writes the survivors.
 // B.nb_slot[0..8) holds the pool slots of the block and its seven upper neighbours (-1 = absent), `present` the same as bits.
-// REV 1 keeps the cube index of every voxel that has triangles (one byte per voxel per warp) so that the emit pass does not
-// rebuild it from eight shared-memory reads per candidate triangle; REV 0 has no such array.
-template <int REV> struct CubeCache { __device__ static __forceinline__ unsigned char* get(int) { return nullptr; } };
-template <> struct CubeCache<1> {
-  __device__ static __forceinline__ unsigned char* get(int wid) { __shared__ unsigned char s_cube[MC_WARPS][BLOCK_VOX]; return s_cube[wid]; }
-};
-
-template <bool SHARDED, int REV>
+// cube_cache keeps the cube index of every voxel that has triangles (one byte per voxel per warp) so that the emit pass does not
+// rebuild it from eight shared-memory reads per candidate triangle.
+template <bool SHARDED>
 __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D, const int slot, const unsigned present, const int (&halo)[7],
                                           float* tile, unsigned short* wlist, unsigned char* cube_cache, const signed char* s_tri, const unsigned char* s_ntri,
                                           const bool color, unsigned long long* __restrict__ out_offset, int* __restrict__ out_count,
@@ -236,7 +208,7 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
       if ((okbits >> need) & 1u) {
         const int ci = cube_index(tile, lx, ly, lz);
         nt = s_ntri[ci];                                                         // 0 for cube index 0 and 255
-        if (REV == 1 && nt > 0) cube_cache[t] = (unsigned char)ci;
+        if (nt > 0) cube_cache[t] = (unsigned char)ci;
       }
       if (!__any_sync(0xffffffffu, nt > 0)) continue;
       int incl = nt;
@@ -270,16 +242,10 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
           const int item = wl[e];
           const int t = item >> 3, k = item & 7;
           const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
-          const signed char* row = s_tri + (REV == 1 ? (int)cube_cache[t] : cube_index(tile, lx, ly, lz)) * 16 + 3 * k;
-          if (REV == 1) {
-            const EdgeFetch f0 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[0], color), f1 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[1], color),
-                            f2 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[2], color);
-            p0 = edge_finish(B, f0, color); p1 = edge_finish(B, f1, color); p2 = edge_finish(B, f2, color);
-          } else {
-            p0 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[0], color);
-            p1 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[1], color);
-            p2 = edge_vertex<SHARDED>(B, D, lx, ly, lz, row[2], color);
-          }
+          const signed char* row = s_tri + (int)cube_cache[t] * 16 + 3 * k;
+          const EdgeFetch f0 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[0], color), f1 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[1], color),
+                          f2 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[2], color);
+          p0 = edge_finish(B, f0, color); p1 = edge_finish(B, f1, color); p2 = edge_finish(B, f2, color);
           valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -304,11 +270,10 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
 // room scan most of the working set is free space, so most blocks end here without their voxels being read. Survivors
 // are appended to a work queue (block, slot, the eight corner-block slots and owners), which decouples meshing from the
 // list order: surface blocks are clustered in the list, and a warp that drew four of them used to serialise them.
-// REV 1 (opt-in, VH_MC_REV=1): the neighbour look-up reads key, stamp and slot of the FIRST probe position together (three
-// independent loads; at the table's load factor nine look-ups in ten end there) instead of key -> stamp/slot one after
-// the other, which shortens the chain of dependent loads the filter spends its time waiting on. Later probe positions
-// (rare) take the ordinary path. Same results.
-template <bool SHARDED, int REV = 0>
+// The neighbour look-up reads key, stamp and slot of the FIRST probe position together (three independent loads; at the
+// table's load factor nine look-ups in ten end there) instead of key -> stamp/slot one after the other, which shortens the
+// chain of dependent loads the filter spends its time waiting on. Later probe positions (rare) take the ordinary path.
+template <bool SHARDED>
 __global__ void __launch_bounds__(256)
 mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int* __restrict__ list,
                  const int* __restrict__ list_count, const int full_map, unsigned long long* __restrict__ out_offset,
@@ -342,18 +307,13 @@ mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D,
           const PeerView P = D.peers->v[nb_owner];
           t_keys = P.keys; t_slots = P.slots; t_stamps = P.stamps; t_neg = P.neg_count; t_mask = P.mask;
         }
-        if (REV == 1) {
-          const uint32_t h0 = hash_key(nk) & t_mask;
-          const u64 k0 = __ldcg(&t_keys[h0]);
-          uint32_t st = t_stamps[h0];
-          int sl = t_slots[h0];
-          int e = k0 == nk ? (int)h0 : -1;
-          if (k0 != nk && k0 != KEY_EMPTY) { e = map_find_in(t_keys, t_mask, nk); if (e >= 0) { st = t_stamps[e]; sl = t_slots[e]; } }
-          if (e >= 0 && (full_map || st == frame)) { nb = sl; if (nb >= 0) nneg = t_neg[nb]; }
-        } else {
-          const int e = map_find_in(t_keys, t_mask, nk);
-          if (e >= 0 && (full_map || t_stamps[e] == frame)) { nb = t_slots[e]; if (nb >= 0) nneg = t_neg[nb]; }
-        }
+        const uint32_t h0 = hash_key(nk) & t_mask;
+        const u64 k0 = __ldcg(&t_keys[h0]);
+        uint32_t st = t_stamps[h0];
+        int sl = t_slots[h0];
+        int e = k0 == nk ? (int)h0 : -1;
+        if (k0 != nk && k0 != KEY_EMPTY) { e = map_find_in(t_keys, t_mask, nk); if (e >= 0) { st = t_stamps[e]; sl = t_slots[e]; } }
+        if (e >= 0 && (full_map || st == frame)) { nb = sl; if (nb >= 0) nneg = t_neg[nb]; }
       }
     }
     const unsigned gsh = grp * 8;
@@ -382,7 +342,7 @@ mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D,
 // Persistent warps pull blocks off the work queue (one atomicAdd per block) and mesh them: perfect balance whatever the
 // spatial clustering of surface blocks. The last thing the kernel does is clear the OTHER queue-control slot, which the
 // next launch pair will use (the two slots alternate, so no memset node is needed per frame).
-template <bool SHARDED, int REV = 0>
+template <bool SHARDED>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int full_map, unsigned long long* __restrict__ out_offset,
                int* __restrict__ out_count, const McWork* __restrict__ queue, McQueueCtl* __restrict__ ctl, McQueueCtl* __restrict__ ctl_next,
@@ -393,6 +353,7 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
   __shared__ unsigned short s_list[MC_WARPS][BLOCK_VOX * 5];   // candidate triangles of the block in flight
   __shared__ __align__(16) signed char s_tri[256 * 16];
   __shared__ __align__(16) unsigned char s_ntri[256];
+  __shared__ unsigned char s_cube[MC_WARPS][BLOCK_VOX];        // cube index of the voxels that have triangles
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int total = ctl->count;
@@ -433,7 +394,7 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
     __syncwarp();                              // previous block's readers of s_nb / tile / list are done
     if (lane < 8) { s_nb[wid][lane] = w->nb[lane]; s_nbo[wid][lane] = SHARDED ? (int)w->owner[lane] : 0; }
     __syncwarp();
-    my_tris += (unsigned long long)mesh_block<SHARDED, REV>(C, D, cur_slot, present, halo, tile, s_list[wid], CubeCache<REV>::get(wid), s_tri, s_ntri, color, out_offset, out_count, lane, frame);
+    my_tris += (unsigned long long)mesh_block<SHARDED>(C, D, cur_slot, present, halo, tile, s_list[wid], s_cube[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
@@ -447,21 +408,17 @@ void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const De
   McQueueCtl* ctl_next = D.mc_ctl + ((*D.mc_parity & 1) ^ 1);
   *D.mc_parity ^= 1;
   // launch shapes; the environment overrides exist for sweeps on the GPU box (both kernels are latency-bound: the filter
-  // walks chains of dependent look-ups at 26 registers per thread, so 8 CTAs per SM fit)
-  static const int filter_ctas = [] { const char* v = getenv("VH_MC_FILTER_CTAS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 8 ? n : 4; }();
+  // walks chains of dependent look-ups at 26 registers per thread, so 8 CTAs per SM fit: 0.069 -> 0.063 ms per frame against 4, profiles/r02a)
+  static const int filter_ctas = [] { const char* v = getenv("VH_MC_FILTER_CTAS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 8 ? n : 8; }();
   static const int mesh_ctas = [] { const char* v = getenv("VH_MC_MESH_CTAS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 6 ? n : 5; }();
   const int fgrid = num_sms * filter_ctas;
   const int mgrid = num_sms * mesh_ctas;         // 5 CTAs of 4 warps fit an SM (36.7 KB of shared memory each)
   if (S.shard_count > 1 && D.peers) {
-    if (S.mc_rev == 1) mc_filter_kernel<true, 1><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    else mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    if (S.mc_rev == 1) mc_mesh_kernel<true, 1><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
-    else mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
   } else {
-    if (S.mc_rev == 1) mc_filter_kernel<false, 1><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    else mc_filter_kernel<false><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    if (S.mc_rev == 1) mc_mesh_kernel<false, 1><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
-    else mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    mc_filter_kernel<false><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
+    mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
   }
 }
 #endif  // !VH_HOST_EMU

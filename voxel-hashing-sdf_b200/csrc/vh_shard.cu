@@ -1,14 +1,20 @@
 // vh_shard.cu — one map sharded over several B200s (BASELINE config 4): one engine per process and GPU, block
-// ownership by a hash of the block coordinate, frames broadcast from rank 0 with NCCL, marching-cubes halos read
-// straight out of the owner GPU's memory over NVLink, meshes gathered on rank 0.
-//
-// The reference has no multi-GPU path (one global pair of tables, no cudaSetDevice); this is new.
-//   * vh_shard_connect: NCCL communicator (ncclCommInitRank) + an all-gather of CUDA-IPC handles of every rank's table
-//     and voxel planes. Each process maps its peers' allocations (cudaIpcOpenMemHandle) and uploads the PeerTable the
-//     sharded marching-cubes kernel walks: a neighbour block is looked up in the table of the GPU its key hashes to.
-//   * vh_integrate_sharded: ncclBroadcast of {pose, depth, rgb} from rank 0 on the engine's stream, then the normal
-//     frame pipeline with the owner filter in the allocation kernel; around marching cubes two stream-ordered NCCL
-//     barriers keep any GPU from meshing against voxels another GPU is still (or already again) integrating.
+// ownership by a hash of the block coordinate, every GPU allocates, integrates and meshes only its own blocks, meshes
+// gathered on rank 0. The reference has no multi-GPU path (one global pair of tables, no cudaSetDevice); this is new.
+//   * vh_shard_connect: NCCL communicator (ncclCommInitRank) + an all-gather of CUDA-IPC handles: every process maps its peers'
+//     tables, voxel planes, key inboxes, flag words and rank 0's frame ring (cudaIpcOpenMemHandle) — NVLink peer memory that
+//     the kernels address directly.
+//   * vh_integrate_sharded / vh_integrate_sharded_device, per frame (collective, same order on every rank):
+//       rank 0 puts {pose, depth, rgb} into a slot of its frame ring (H2D from the caller's host buffers on the upload stream,
+//       double-buffered, or one device copy) and raises a sequence flag in every peer's memory;
+//       every GPU's pack_frame_kernel READS THE FRAME OUT OF RANK 0'S MEMORY OVER NVLINK while packing it — broadcast and
+//       first compute step are one kernel, there is no staging copy and no collective launch (VH_SHARD_BCAST=nccl selects the
+//       ncclBroadcast of round 1 instead, kept as the baseline: it costs a ~100 us serial chain per frame);
+//       ray_keys_kernel: the rays are SPLIT across the GPUs; every key goes to its owner's inbox with NVLink stores;
+//       frame barrier; insert_keys_kernel on the own inbox; work list; integrate of the own blocks;
+//       second barrier; marching cubes — neighbour blocks are looked up in the table of the GPU their key hashes to and
+//       their sdf / colour halos are read from that GPU's planes, inside the kernels.
+//     The barrier that keeps a GPU from integrating frame f+1 while a peer still meshes frame f is the first barrier of frame f+1.
 //   * vh_shard_gather_mesh: every rank's ordered per-block triangle ranges go to rank 0 (ncclSend/ncclRecv), which
 //     merges them by the reference's mesh order (tsdf2mesh, tsdf.cu:1786-1806) — identical to the one-GPU soup.
 // NCCL is bound at run time (dlopen/dlsym) so that a process that already carries an NCCL (e.g. the one PyTorch
@@ -66,7 +72,8 @@ int load_nccl() {
     if (_r != ncclSuccess) return fail(VH_ERR_CUDA, "NCCL Error: %s at %s:%d (%s)", g_nccl.GetErrorString(_r), __FILE__, __LINE__, #call); \
   } while (0)
 
-constexpr int N_SHARED = 7;     // keys, slots, stamps, neg_count, sdf, rgb, barrier flags
+constexpr int N_SHARED = 10;    // keys, slots, stamps, neg_count, sdf, rgb, flag words, key inbox, inbox counters, frame ring
+constexpr int FLAG_WORDS = 2 * MAX_SHARDS;      // [0, MAX_SHARDS): barrier arrival epochs; [MAX_SHARDS]: sequence number of the newest frame in rank 0's ring
 struct ShardExport {
   cudaIpcMemHandle_t h[N_SHARED];
   uint32_t capacity; int pool_blocks; int has_rgb; int device;
@@ -78,13 +85,17 @@ struct vh_shard_state {
   ncclComm_t comm = nullptr;
   int rank = 0, count = 1;
   void* mapped[MAX_SHARDS][N_SHARED] = {};
-  uint8_t* d_frame = nullptr;         // broadcast buffer: {c2w[16] f32 | depth f32[H*W] | rgb u8[H*W*3]}, double-buffered
+  uint8_t* d_frame = nullptr;         // frame ring: {c2w[16] f32 | depth f32[H*W] | rgb u8[H*W*3]} x 2 slots; rank 0's is mapped by every peer
+  const uint8_t* frame_src = nullptr; // where this rank's kernels read frames from: rank 0's ring (pull) or the own ring (NCCL broadcast)
+  bool pull = true;                   // frames are read out of rank 0's memory by the pack kernel (default); false: ncclBroadcast into the own ring
+  cudaEvent_t released[2] = {nullptr, nullptr};   // rank 0: every GPU is past the frame barrier of the slot's previous frame (nobody reads it any more)
+  uint64_t frame_seq = 0;             // frames put into the ring so far
   size_t frame_bytes = 0;
   uint8_t* h_frame = nullptr;         // pinned staging of the same layout (rank 0 packs the caller's buffers here)
   int ring = 0;
   cudaEvent_t consumed[2] = {nullptr, nullptr}, uploaded[2] = {nullptr, nullptr}, arrived[2] = {nullptr, nullptr}; bool used[2] = {false, false};
   int* d_token = nullptr;             // 1-int all-reduce (connect-time barrier)
-  uint32_t* d_flags = nullptr;        // [MAX_SHARDS] arrival epochs written by the peers (and by this GPU) over NVLink
+  uint32_t* d_flags = nullptr;        // [FLAG_WORDS] arrival epochs written by the peers (and by this GPU) over NVLink, frame sequence flag
   uint32_t* peer_flags[MAX_SHARDS] = {};
   uint32_t epoch = 0;
   float* h_pose = nullptr;            // pinned: pose read back on ranks that were not given one
@@ -93,6 +104,7 @@ struct vh_shard_state {
 void shard_release(vh_engine* e) {
   vh_shard_state* s = e->shard;
   if (!s) return;
+  if (e->stream && s->peer_flags[s->rank]) shard_barrier(e);      // no peer is still reading this GPU's memory (a dead peer costs the 4 s watchdog)
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->upload) cudaStreamSynchronize(e->upload);
   for (int r = 0; r < s->count; r++)
@@ -106,6 +118,7 @@ void shard_release(vh_engine* e) {
     if (s->consumed[i]) cudaEventDestroy(s->consumed[i]);
     if (s->uploaded[i]) cudaEventDestroy(s->uploaded[i]);
     if (s->arrived[i]) cudaEventDestroy(s->arrived[i]);
+    if (s->released[i]) cudaEventDestroy(s->released[i]);
   }
   cudaFree(e->d_peers); e->d_peers = nullptr; e->D.peers = nullptr;
   delete s;
@@ -129,13 +142,29 @@ __global__ void shard_barrier_kernel(FlagPtrs peers, uint32_t* __restrict__ mine
     __threadfence_system();
   }
 }
-static int shard_barrier(vh_engine* e) {
+int shard_barrier(vh_engine* e) {
   vh_shard_state* s = e->shard;
   FlagPtrs fp;
   for (int q = 0; q < MAX_SHARDS; q++) fp.p[q] = s->peer_flags[q];
   shard_barrier_kernel<<<1, 32, 0, e->stream>>>(fp, s->d_flags, s->rank, s->count, ++s->epoch, e->D.engine_error);
   return VH_OK;
 }
+// rank 0, on its upload stream behind the copies of frame `seq` into the ring: tell every GPU the frame is there
+__global__ void frame_ready_kernel(FlagPtrs peers, int n, uint32_t seq) {
+  const int t = threadIdx.x;
+  if (t < n) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(peers.p[t] + MAX_SHARDS) = seq; }
+}
+// every other GPU, on its compute stream ahead of the frame's first kernel
+__global__ void frame_wait_kernel(const uint32_t* __restrict__ mine, uint32_t seq, int* __restrict__ error) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while ((int)(*reinterpret_cast<const volatile uint32_t*>(mine + MAX_SHARDS) - seq) < 0) {
+      if (clock64() - t0 > 8000000000ll) { atomicOr(error, 8); break; }     // ~4 s: rank 0 died; never hang the GPU
+    }
+    __threadfence_system();
+  }
+}
+
 static int nccl_barrier(vh_engine* e) {
   vh_shard_state* s = e->shard;
   NK(g_nccl.AllReduce(s->d_token, s->d_token, 1, ncclInt, ncclSum, s->comm, e->stream));
@@ -183,18 +212,20 @@ int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]) {
   CK(cudaHostAlloc((void**)&s->h_pose, 2 * 16 * sizeof(float), cudaHostAllocDefault));
   CK(cudaMalloc((void**)&s->d_token, sizeof(int)));
   CK(cudaMemset(s->d_token, 0, sizeof(int)));
-  CK(cudaMalloc((void**)&s->d_flags, MAX_SHARDS * sizeof(uint32_t)));
-  CK(cudaMemset(s->d_flags, 0, MAX_SHARDS * sizeof(uint32_t)));
+  CK(cudaMalloc((void**)&s->d_flags, FLAG_WORDS * sizeof(uint32_t)));
+  CK(cudaMemset(s->d_flags, 0, FLAG_WORDS * sizeof(uint32_t)));
+  { const char* v = getenv("VH_SHARD_BCAST"); s->pull = !(v && v[0] == 'n'); }      // VH_SHARD_BCAST=nccl: the ncclBroadcast route
   for (int i = 0; i < 2; i++) {
     CK(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s->uploaded[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s->arrived[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->released[i], cudaEventDisableTiming));
   }
 
   // exchange IPC handles of what a peer's marching cubes needs to read
   ShardExport mine;
   memset(&mine, 0, sizeof(mine));
-  void* ptrs[N_SHARED] = {e->D.map.keys, e->D.map.slots, e->D.stamps, e->D.neg_count, e->D.sdf, e->D.rgb, s->d_flags};
+  void* ptrs[N_SHARED] = {e->D.map.keys, e->D.map.slots, e->D.stamps, e->D.neg_count, e->D.sdf, e->D.rgb, s->d_flags, e->D.inbox, e->D.inbox_count, s->d_frame};
   for (int k = 0; k < N_SHARED; k++)
     if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
   mine.capacity = e->capacity; mine.pool_blocks = e->P.pool_blocks; mine.has_rgb = e->D.rgb ? 1 : 0; mine.device = e->P.device;
@@ -216,6 +247,7 @@ int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]) {
     for (int k = 0; k < N_SHARED; k++) {
       if (q == r) m[k] = ptrs[k];
       else if (k == 5 && !all[q].has_rgb) m[k] = nullptr;
+      else if (k == 9 && q != 0) m[k] = nullptr;                  // only rank 0's frame ring is read by its peers
       else {
         cudaError_t ce = cudaIpcOpenMemHandle(&m[k], all[q].h[k], cudaIpcMemLazyEnablePeerAccess);
         if (ce != cudaSuccess) return fail(VH_ERR_CUDA, "CUDA Error: cannot map shard %d's memory (%s): the GPUs need peer access (NVLink/NVSwitch)", q, cudaGetErrorString(ce));
@@ -225,7 +257,9 @@ int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]) {
     PeerView& v = pt.v[q];
     v.keys = (const u64*)m[0]; v.slots = (const int*)m[1]; v.stamps = (const uint32_t*)m[2]; v.neg_count = (const int*)m[3];
     v.sdf = (const float*)m[4]; v.rgb = (const uchar4*)m[5]; v.mask = e->capacity - 1;
+    v.inbox = (u64*)m[7]; v.inbox_count = (int*)m[8];
     s->peer_flags[q] = (uint32_t*)m[6];
+    if (q == 0) s->frame_src = s->pull ? (const uint8_t*)m[9] : s->d_frame;
   }
   CK(cudaMalloc((void**)&e->d_peers, sizeof(PeerTable)));
   CK(cudaMemcpy(e->d_peers, &pt, sizeof(pt), cudaMemcpyHostToDevice));
@@ -237,11 +271,10 @@ int vh_shard_connect(vh_engine* e, const uint8_t id[VH_NCCL_ID_BYTES]) {
 }
 
 // One frame on every GPU of the group (collective: every rank calls it, in the same order). depth / rgb are read on
-// rank 0 only (host pointers, like vh_integrate); c2w may be NULL on the other ranks, which then take the pose out of
-// the broadcast (one small D2H + stream sync per frame on those ranks; pass the pose everywhere to stay asynchronous).
-int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
-  if (!e) return fail(VH_ERR_INVALID, "null engine");
-  std::lock_guard<std::mutex> lk(e->mtx);
+// rank 0 only (host pointers like vh_integrate, or device pointers for vh_integrate_sharded_device); c2w may be NULL on the
+// other ranks, which then take the pose out of the frame (one small D2H + stream sync per frame on those ranks; pass the pose
+// everywhere to stay asynchronous).
+static int integrate_sharded_common(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w, bool host_inputs) {
   vh_shard_state* s = e->shard;
   if (!s) return fail(VH_ERR_INVALID, "vh_shard_connect has not been called");
   if (s->rank == 0 && (!depth || !c2w)) return fail(VH_ERR_INVALID, "rank 0 must supply depth and pose");
@@ -250,70 +283,118 @@ int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, c
   if (rc != VH_OK) return rc;
   const size_t npx = (size_t)e->P.width * e->P.height;
   const int b = s->ring & 1; s->ring++;
-  uint8_t* dbuf = s->d_frame + (size_t)b * s->frame_bytes;
+  const uint32_t seq = (uint32_t)(++s->frame_seq);
+  uint8_t* dbuf = s->d_frame + (size_t)b * s->frame_bytes;                       // own ring slot (rank 0: the slot everybody reads)
   const bool with_rgb = e->S.use_color != 0;                      // group-wide: every rank was created with the same flag
   const size_t bytes = 64 + npx * 4 + (with_rgb ? npx * 3 : 0);
   CK(cudaEventRecord(e->ev[0], e->stream));
-  // Upload and broadcast run on the upload stream, double-buffered: frame k+1 travels (PCIe, then NVLink) while frame k is
-  // still being integrated and meshed; the compute stream only waits for the broadcast of its own frame.
+  // Rank 0 fills the slot on its upload stream, double-buffered: frame k+1 arrives over PCIe while frame k is being integrated and
+  // meshed. The slot's previous frame (k-1) is no longer read once every GPU is past frame k-1's barrier (`released`).
   cudaStream_t up = e->upload;
-  if (s->used[b]) CK(cudaStreamWaitEvent(up, s->consumed[b], 0));            // buffer b's previous frame has been consumed
+  if (s->rank == 0 || !s->pull) { if (s->used[b]) CK(cudaStreamWaitEvent(up, s->pull ? s->released[b] : s->consumed[b], 0)); }
   if (s->rank == 0) {
-    // pinned caller buffers are copied straight into the broadcast buffer; pageable ones go through the pinned staging slot
-    cudaPointerAttributes pa;
-    const bool pinned = cudaPointerGetAttributes(&pa, depth) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
-                        (!with_rgb || !rgb || (cudaPointerGetAttributes(&pa, rgb) == cudaSuccess && pa.type == cudaMemoryTypeHost));
-    cudaGetLastError();
     uint8_t* hbuf = s->h_frame + (size_t)b * s->frame_bytes;
     if (s->used[b]) CK(cudaEventSynchronize(s->uploaded[b]));    // staging slot b's previous upload (two frames ago) has left the host
     memcpy(hbuf, c2w, 64);
     CK(cudaMemcpyAsync(dbuf, hbuf, 64, cudaMemcpyHostToDevice, up));
-    if (pinned) {
-      CK(cudaMemcpyAsync(dbuf + 64, depth, npx * 4, cudaMemcpyHostToDevice, up));
-      if (with_rgb) { if (rgb) CK(cudaMemcpyAsync(dbuf + 64 + npx * 4, rgb, npx * 3, cudaMemcpyHostToDevice, up)); else CK(cudaMemsetAsync(dbuf + 64 + npx * 4, 0, npx * 3, up)); }
+    if (!host_inputs) {
+      CK(cudaMemcpyAsync(dbuf + 64, depth, npx * 4, cudaMemcpyDeviceToDevice, up));
+      if (with_rgb) { if (rgb) CK(cudaMemcpyAsync(dbuf + 64 + npx * 4, rgb, npx * 3, cudaMemcpyDeviceToDevice, up)); else CK(cudaMemsetAsync(dbuf + 64 + npx * 4, 0, npx * 3, up)); }
     } else {
-      memcpy(hbuf + 64, depth, npx * 4);
-      if (with_rgb) { if (rgb) memcpy(hbuf + 64 + npx * 4, rgb, npx * 3); else memset(hbuf + 64 + npx * 4, 0, npx * 3); }
-      CK(cudaMemcpyAsync(dbuf + 64, hbuf + 64, bytes - 64, cudaMemcpyHostToDevice, up));
+      // pinned caller buffers are copied straight into the ring; pageable ones go through the pinned staging slot
+      cudaPointerAttributes pa;
+      const bool pinned = cudaPointerGetAttributes(&pa, depth) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                          (!with_rgb || !rgb || (cudaPointerGetAttributes(&pa, rgb) == cudaSuccess && pa.type == cudaMemoryTypeHost));
+      cudaGetLastError();
+      if (pinned) {
+        CK(cudaMemcpyAsync(dbuf + 64, depth, npx * 4, cudaMemcpyHostToDevice, up));
+        if (with_rgb) { if (rgb) CK(cudaMemcpyAsync(dbuf + 64 + npx * 4, rgb, npx * 3, cudaMemcpyHostToDevice, up)); else CK(cudaMemsetAsync(dbuf + 64 + npx * 4, 0, npx * 3, up)); }
+      } else {
+        memcpy(hbuf + 64, depth, npx * 4);
+        if (with_rgb) { if (rgb) memcpy(hbuf + 64 + npx * 4, rgb, npx * 3); else memset(hbuf + 64 + npx * 4, 0, npx * 3); }
+        CK(cudaMemcpyAsync(dbuf + 64, hbuf + 64, bytes - 64, cudaMemcpyHostToDevice, up));
+      }
     }
     CK(cudaEventRecord(s->uploaded[b], up));
+    if (s->pull) {      // the frame is in the ring: raise the sequence flag in every GPU's memory
+      FlagPtrs fp;
+      for (int q = 0; q < MAX_SHARDS; q++) fp.p[q] = s->peer_flags[q];
+      frame_ready_kernel<<<1, 32, 0, up>>>(fp, s->count, seq);
+    }
   }
-  NK(g_nccl.Broadcast(dbuf, dbuf, bytes, ncclChar, 0, s->comm, up));
-  CK(cudaEventRecord(s->arrived[b], up));
-  CK(cudaStreamWaitEvent(e->stream, s->arrived[b], 0));
+  const uint8_t* src = s->pull ? s->frame_src + (size_t)b * s->frame_bytes : dbuf;
+  if (s->pull) {
+    if (s->rank == 0) { CK(cudaEventRecord(s->arrived[b], up)); CK(cudaStreamWaitEvent(e->stream, s->arrived[b], 0)); }
+    else frame_wait_kernel<<<1, 32, 0, e->stream>>>(s->d_flags, seq, e->D.engine_error);
+  } else {
+    NK(g_nccl.Broadcast(dbuf, dbuf, bytes, ncclChar, 0, s->comm, up));
+    CK(cudaEventRecord(s->arrived[b], up));
+    CK(cudaStreamWaitEvent(e->stream, s->arrived[b], 0));
+  }
   CK(cudaEventRecord(e->ev[1], e->stream));
   float pose[16];
   if (c2w) memcpy(pose, c2w, sizeof(pose));
   else {
-    CK(cudaMemcpyAsync(s->h_pose, dbuf, 64, cudaMemcpyDeviceToHost, up));
-    CK(cudaStreamSynchronize(up));
+    CK(cudaMemcpyAsync(s->h_pose, src, 64, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     memcpy(pose, s->h_pose, sizeof(pose));
   }
-  e->cur_depth = reinterpret_cast<const float*>(dbuf + 64);
-  e->cur_rgb = with_rgb ? dbuf + 64 + npx * 4 : nullptr;
+  e->cur_depth = reinterpret_cast<const float*>(src + 64);                      // rank 0's memory in pull mode: read over NVLink by the kernels below
+  e->cur_rgb = with_rgb ? src + 64 + npx * 4 : nullptr;
   setup_frame(e, pose);
-  // allocate (own blocks only) + integrate, then marching cubes between two barriers
   DeviceView& D = e->D;
   uint2* px = e->d_px[e->px_ring & 1]; e->px_ring++;
+  static const int dbg = getenv("VH_SHARD_DEBUG") ? atoi(getenv("VH_SHARD_DEBUG")) : 0;   // timing experiments only: 1 = no barriers, 2 = local-only MC
   launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, D.tile_max, D.sched, D.counters, e->F.frame, e->stream);
-  launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);
+  if (alloc_uses_inbox(e->S)) {
+    // the rays are split across the GPUs, their keys travel to the owners' inboxes; once every GPU is past the barrier all keys
+    // of the frame have arrived (and every GPU has finished meshing the previous frame: its voxels may change again)
+    launch_ray_keys(e->S, e->F, e->cur_depth, D, e->num_sms, e->stream);
+    if (!(dbg & 1)) { rc = shard_barrier(e); if (rc != VH_OK) return rc; }
+    launch_insert_keys(e->S, e->F, D, e->num_sms, e->stream);
+  } else {
+    if (!(dbg & 1)) { rc = shard_barrier(e); if (rc != VH_OK) return rc; }
+    launch_alloc_visible(e->S, e->F, e->cur_depth, D, e->stream);              // replicated ray pass with an owner filter
+  }
+  if (s->rank == 0 && s->pull) CK(cudaEventRecord(s->released[b ^ 1], e->stream));   // every GPU has left the previous frame: its slot may be refilled
+  CK(cudaEventRecord(e->ev[5], e->stream));
+  launch_cull_list(e->S, e->F, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[2], e->stream));
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->P.mc_per_frame) {
-    static const int dbg = getenv("VH_SHARD_DEBUG") ? atoi(getenv("VH_SHARD_DEBUG")) : 0;   // timing experiments only: 1 = no barriers, 2 = local-only MC
     if (!(dbg & 1)) { rc = shard_barrier(e); if (rc != VH_OK) return rc; }      // every GPU has integrated frame f
     DeviceView Dm = D;
     if (dbg & 2) Dm.peers = nullptr;
     launch_marching_cubes(e->S, e->F, Dm, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, e->num_sms, e->stream);
-    if (!(dbg & 1)) { rc = shard_barrier(e); if (rc != VH_OK) return rc; }      // every GPU has meshed frame f: voxels may change again
   }
   CK(cudaEventRecord(e->ev[4], e->stream));
   CK(cudaEventRecord(s->consumed[b], e->stream));
   s->used[b] = true;
   e->frames_in_flight++;
   return enqueue_readback(e);
+}
+
+int vh_integrate_sharded(vh_engine* e, const float* depth, const uint8_t* rgb, const float* c2w) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  return integrate_sharded_common(e, depth, rgb, c2w, true);
+}
+// the same with the frame already resident in rank 0's HBM (device pointers on rank 0; ignored elsewhere)
+int vh_integrate_sharded_device(vh_engine* e, const float* d_depth, const uint8_t* d_rgb, const float* c2w) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  return integrate_sharded_common(e, d_depth, d_rgb, c2w, false);
+}
+// every GPU of the group is past everything enqueued before this call on every other GPU (collective, asynchronous): call it
+// before anything outside the frame calls changes voxels that a peer's marching cubes may still be reading (vh_reset does).
+int vh_shard_barrier(vh_engine* e) {
+  if (!e) return fail(VH_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  if (!e->shard) return fail(VH_ERR_INVALID, "vh_shard_connect has not been called");
+  CK(cudaSetDevice(e->P.device));
+  return shard_barrier(e);
 }
 
 // group-wide sums of the last frame's counters (collective)
