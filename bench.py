@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-mc", action="store_true", help="integration only (F_int); default runs working-set MC every frame like the reference")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-frames", action="store_true", help="config 4: the whole 100-frame sequence (~90 M blocks: needs 8 GPUs and --pool-blocks 100663296)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="--gpus 1: skip the reference's own CUDA build (oracle/_ref/libref_cuda_*.so) baseline")
     ap.add_argument("--no-c4", action="store_true", help="--gpus 1: skip the room-scale config 4 side measurement (16 frames on one GPU)")
     ap.add_argument("--ray-steps", type=int, default=0, help="max_ray_steps; 0 = the reference's 100 (configs 3/4: ~1100 reach the walls, SURVEY.md section 8d)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames in one step; 0 = 50 (config 4 with long rays allocates ~0.9 M blocks per frame: use 4)")
@@ -79,7 +81,9 @@ def workload(args, rank):
 
 def config_dict(args, cfg, sc, world):
     return {
-        "workload": f"BASELINE config {args.config[1]}: synthetic {sc.width}x{sc.height} depth+rgb sequence, {sc.n_frames} frames, "
+        "workload": f"BASELINE config {args.config[1]}: synthetic {sc.width}x{sc.height} depth+rgb sequence, {frame_cap(args, sc)} frames"
+                    + (" (the first 16 of 100: ~0.9 M new blocks per frame, 13.4 M blocks = what one GPU holds; cycled when more steps are asked for), " if frame_cap(args, sc) < sc.n_frames else ", ")
+                    + 
                     f"{cfg['vox_size'] * 1000:g} mm voxels, 8^3 blocks, {cfg['num_buckets']}-bucket x4 hash, trunc {cfg['trunc'] * 100:g} cm, MaxDepth {cfg['max_depth']:g}",
         "max_ray_steps": args.ray_steps or 100,
         "frames_per_step": FRAMES_PER_STEP,
@@ -126,14 +130,16 @@ def run_reference_arm(args):
         return
     synth, cfg, sc = workload(args, 0)
     per_step = 1   # bounded sample: one frame of the sequence per step
-    fps, dt, threads, n = cpu_reference_run(args, args.steps + args.warmup, per_step, args.steps, args.warmup)
+    warm = min(args.warmup, 1) if args.config == "C4" else args.warmup      # a room-scale frame takes the host cores several seconds
+    fps, dt, threads, n = cpu_reference_run(args, min(args.steps + warm, frame_cap(args, sc)), per_step, args.steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1000.0 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, cfg, sc, 1),
+        "scaling_note": "the reference has no multi-GPU path: one process on the host cores at every --gpus N",
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} consecutive frames of the workload (1 frame per step, frames {args.warmup}..{args.warmup + n - 1}), "
+                         "sample": f"{n} frames of the workload (1 frame per step" + (", every step from an empty map, 1 warm-up frame" if args.config == "C4" else f", frames {args.warmup}..{args.warmup + n - 1}") + "), "
                                    f"oracle/vh_oracle.c (CPU restatement of the reference's processFrame, pinned against its emulated tsdf.cu) with OpenMP on {threads} threads"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -204,7 +210,7 @@ def run_ours(args):
     W, H = sc.width, sc.height
     n_timed = args.steps * FRAMES_PER_STEP
     n_warm = args.warmup * FRAMES_PER_STEP
-    n_frames = min(max(n_timed, n_warm), sc.n_frames)
+    n_frames = min(max(n_timed, n_warm), frame_cap(args, sc))
 
     # ---- synthetic frames: pinned host copies (e2e) and HBM-resident copies (value) ----
     h_depth = torch.empty((n_frames, H, W), dtype=torch.float32).pin_memory()
@@ -442,11 +448,15 @@ def run_ours(args):
             s4 = synth.make_scene("C4", color=color)
             fps4 = C4_DEFAULTS["frames_per_step"]
             line["room_scale"] = dict(single_gpu_run(vh, torch, np, "C4", c4, s4, color, not args.no_mc, local, fps4, 4 * fps4, C4_DEFAULTS["ray_steps"],
-                                                     C4_DEFAULTS["pool_blocks"]), n_gpus=1,
+                                                     C4_DEFAULTS["pool_blocks"], max_frames=C4_DEFAULTS["frames"]), n_gpus=1,
                                       workload="BASELINE config 4: 640x480, 2 mm voxels, 10 m room centred on the origin, 2^24-bucket x4 hash, trunc 1 cm, "
                                                "max_ray_steps 1100, first 16 frames (~0.9 M new blocks per frame: the 100-frame map does not fit one GPU)")
         except Exception as ex:
             line["room_scale"] = {"error": f"{type(ex).__name__}: {ex}"}
+    # ---- north_star's first baseline: the reference's OWN CUDA build on this box (oracle/build_ref_cuda.sh compiles its src/tsdf.cu for
+    #      sm_100a; oracle/tools/bench_ref_cuda.py drives its processFrame and this engine's vh_integrate over the same frames) ----
+    if world == 1 and args.config == "C2" and not args.no_ref_cuda:
+        line["ref_cuda_baseline"] = ref_cuda_baseline()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             fps, dt, threads, n = cpu_reference_run(args, args.cpu_frames, 1, args.cpu_frames, 0)
@@ -462,6 +472,31 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def ref_cuda_baseline():
+    """The reference's own CUDA build (baseline only, never the optimisation target). One subprocess per config: the reference keeps
+    its tables in file-scope globals (tsdf.cu:19-20). Config 2 is outside what the reference can run (see `config2`)."""
+    out = {"config2": "not runnable by the reference build: at 5 mm its stream-in stage would upload ~3.6 M blocks (22 GB) per frame into a "
+                      "400,000-block heap and keep ~0.5 TB of host triangle slots (SURVEY.md 8(a13), BASELINE.md 3a)"}
+    tool = os.path.join(ROOT, "oracle", "tools", "bench_ref_cuda.py")
+    for cfg_name, frames, warm, variant in (("R8", 4, 1, "8"), ("C1", 2, 1, "8c1")):
+        lib = os.path.join(ROOT, "oracle", "_ref", f"libref_cuda_vpb{variant}.so")
+        if not os.path.exists(lib):
+            out[cfg_name] = {"unavailable": f"{os.path.relpath(lib, ROOT)} not built (oracle/build_ref_cuda.sh needs /root/reference)"}
+            continue
+        try:
+            r = subprocess.run([sys.executable, tool, "--config", cfg_name, "--frames", str(frames), "--warmup", str(warm)], capture_output=True, text=True, timeout=300, cwd=ROOT)
+            js = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if not js:
+                out[cfg_name] = {"error": (r.stderr or r.stdout)[-400:]}
+                continue
+            d = json.loads(js[-1])
+            out[cfg_name] = {k: d[k] for k in ("baseline", "config", "frames_timed", "call", "reference_frames_per_sec", "ours_frames_per_sec", "speedup",
+                                               "faces_reference", "faces_ours", "visible_blocks_reference", "visible_blocks_ours", "note") if k in d}
+        except Exception as ex:
+            out[cfg_name] = {"error": f"{type(ex).__name__}: {ex}"}
+    return out
+
+
 def peak_hbm():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -484,13 +519,14 @@ def make_frames(torch, np, sc, n_frames, color, pinned=True, device=True):
     return h_depth, h_rgb, d_depth, d_rgb, poses
 
 
-def single_gpu_run(vh, torch, np, cfg_name, cfg, sc, color, mc, local, n_warm, n_timed, ray_steps, pool_blocks, frames=None):
+def single_gpu_run(vh, torch, np, cfg_name, cfg, sc, color, mc, local, n_warm, n_timed, ray_steps, pool_blocks, frames=None, max_frames=None):
     """One map on ONE GPU, frames resident in its HBM: frames/s, voxel updates/s and the per-stage times (used for config 4 at
     --gpus 1 and, on rank 0, as the same-run single-GPU point of a multi-GPU run)."""
-    n_frames = min(max(n_timed, n_warm), sc.n_frames)
+    n_frames = min(max(n_timed, n_warm), max_frames or sc.n_frames)
     if frames is None:
         frames = make_frames(torch, np, sc, n_frames, color, pinned=False)
     _, _, d_depth, d_rgb, poses = frames
+    n_frames = len(poses)
     p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"], num_buckets=cfg["num_buckets"],
                             entries_per_bucket=4, pool_blocks=pool_blocks, use_color=1 if color else 0, mc_per_frame=1 if mc else 0, device=local,
                             tri_arena_bytes=4 << 30, **(dict(max_ray_steps=ray_steps) if ray_steps else {}))
@@ -607,7 +643,7 @@ def run_multi(args):
     cfg = synth.CONFIGS[args.config]
     sc = synth.make_scene(args.config, color=color)               # every rank integrates rank 0's trajectory
     n_timed, n_warm = args.steps * FRAMES_PER_STEP, args.warmup * FRAMES_PER_STEP
-    n_frames = min(max(n_timed, n_warm), sc.n_frames)
+    n_frames = min(max(n_timed, n_warm), frame_cap(args, sc))
     pool = args.pool_blocks or (3 << 20)
     frames = make_frames(torch, np, sc, n_frames, color, pinned=(rank == 0), device=(rank == 0))
     sampler = ClockSampler(local) if rank == 0 else None
@@ -684,7 +720,12 @@ def run_multi(args):
     dist.destroy_process_group()
 
 
-C4_DEFAULTS = dict(ray_steps=1100, frames_per_step=4, pool_blocks=16 << 20)    # room scale: the step cap scaled to the block size, ~0.9 M new blocks per frame
+C4_DEFAULTS = dict(ray_steps=1100, frames_per_step=4, pool_blocks=16 << 20, frames=16)    # room scale: the step cap scaled to the block size; ~0.9 M new blocks per
+# frame, so the sequence is the first 16 frames (13.4 M blocks, 80 GB: what ONE GPU holds), cycled when more steps are asked for
+
+
+def frame_cap(args, sc):
+    return min(sc.n_frames, C4_DEFAULTS["frames"]) if args.config == "C4" and not args.all_frames else sc.n_frames
 
 
 def apply_defaults(a):

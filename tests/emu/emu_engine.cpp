@@ -54,7 +54,6 @@ struct emu_engine {
 namespace {
 struct AllocArgs { StaticParams S; FrameParams F; const float* depth; DeviceView D; int tiles_x; };
 void run_alloc(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel(a->S, a->F, a->depth, a->D, a->tiles_x); }
-void run_alloc_r1(void* p) { AllocArgs* a = static_cast<AllocArgs*>(p); alloc_visible_kernel_r1(a->S, a->F, a->depth, a->D, a->tiles_x); }
 struct KeysArgs { StaticParams S; FrameParams F; const float* depth; DeviceView D; int tiles_x, n_tiles; };
 template <int TRX, int TRY> void run_ray_keys(void* p) { KeysArgs* a = static_cast<KeysArgs*>(p); ray_keys_kernel<TRX, TRY>(a->S, a->F, a->depth, a->D, a->tiles_x, a->n_tiles); }
 struct InsertArgs { DeviceView D; uint32_t frame; };
@@ -77,7 +76,7 @@ void run_march_compare(void* p) {
   u64* seq = reinterpret_cast<u64*>(sT + (size_t)RAYS * 3 * K);      // [K][RAYS] keys of the sequential march
   static int s_death[RAYS];
   const int tile_x = blockIdx.x % a->tiles_x, tile_y = blockIdx.x / a->tiles_x;
-  merge_fill_keys(S, a->F, a->depth, tile_x, tile_y, skeys, sT, s_death);
+  merge_fill_keys_t<RAYS_X, RAYS_Y>(S, a->F, a->depth, tile_x, tile_y, skeys, sT, s_death);
   if (tid < RAYS) {
     RayState R;
     ray_setup(S, a->F, a->depth, tile_x * RAYS_X + (tid & (RAYS_X - 1)), tile_y * RAYS_Y + (tid / RAYS_X), R);
@@ -197,8 +196,7 @@ int emu_phase_integrate(emu_engine* e, const float* depth, const uint8_t* rgb, c
     const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;     // launch_alloc_visible
     const size_t smem = 2 * CHUNK_KEYS * sizeof(u64) + (size_t)S.max_steps * RAYS * sizeof(int);
     AllocArgs a{S, e->F, depth, D, tiles_x};
-    if (e->alloc_rev == 1) emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_alloc_r1, &a, alloc_r1_smem_bytes(S.max_steps));
-    else emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_alloc, &a, smem);
+    emu::run_grid(dim3(tiles_x * tiles_y), dim3(ALLOC_THREADS), run_alloc, &a, smem);
   }
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   emu_launch_integrate(e->S, e->F, e->px.data(), D, rgb_in != nullptr, e->rev, 2);

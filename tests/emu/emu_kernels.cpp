@@ -53,7 +53,7 @@ void emu_launch_integrate(const StaticParams& S, const FrameParams& F, const uin
   emu::run_grid(dim3(2), dim3(256), run_cull_list, &ia);
   if (rev == 2) {
     void (*entry)(void*) = !color ? run_staged<false, false, false, 2> : delta ? run_staged<true, false, true, 2> : run_staged<true, false, false, 2>;
-    emu::run_grid(dim3(std::max(ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes());
+    emu::run_grid(dim3(std::max(ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes(2));
   } else {
     void (*entry)(void*) = !color ? run_direct<false, false, false, 3> : delta ? run_direct<true, false, true, 3> : run_direct<true, false, false, 3>;
     emu::run_grid(dim3(std::max(ctas, 1)), dim3(INT_THREADS), entry, &ia);
@@ -124,7 +124,7 @@ int emu_integrate(emu_integrate_io* io) {
     if (io->verify) entry = !color ? PICK2(false, true, false) : delta ? PICK2(true, true, true) : PICK2(true, true, false);
     else entry = !color ? PICK2(false, false, false) : delta ? PICK2(true, false, true) : PICK2(true, false, false);
 #undef PICK2
-    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes());
+    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes(io->two_steps ? 2 : 1));
   } else if (io->variant == 3) {      // integrate_kernel_direct with 64-bit voxel indices
     if (io->verify) entry = !color ? run_direct_wide<false, true, false> : delta ? run_direct_wide<true, true, true> : run_direct_wide<true, true, false>;
     else entry = !color ? run_direct_wide<false, false, false> : delta ? run_direct_wide<true, false, true> : run_direct_wide<true, false, false>;

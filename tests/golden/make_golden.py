@@ -5,7 +5,8 @@ oracle/build_ref.sh). Run here, where /root/reference exists:
 
 Each fixture holds the synthetic-scene parameters (inputs are regenerated deterministically from them), the
 visible block list of every frame, every stored block of the final map (keys, sdf, weight, rgb — only blocks that
-were ever visible) and the final ordered triangle soup. One subprocess per case: the reference keeps its tables in
+were ever visible), the final ordered triangle soup and the bytes of the PLY file the reference's own SavePLY / tsdf2mesh
+(src/tsdf.cu:1697-1708, :1760-1888) writes for that map. One subprocess per case: the reference keeps its tables in
 file-scope globals (tsdf.cu:19-20), so one engine per process.
 """
 import importlib
@@ -45,6 +46,10 @@ def run_case(name):
                n_frames=np.array(case["frames"]))
     for i, k in enumerate(vis):
         out[f"visible_{i}"] = k
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:          # the reference's own mesh export: vertex welding, numbering, ASCII formatting
+        ref.save_ply(os.path.join(td, "model.ply"))
+        out["ply"] = np.frombuffer(open(os.path.join(td, "model.ply"), "rb").read(), np.uint8)
     cs = ref.checksum()
     out["checksum"] = np.array([cs["sum_sdf"], cs["sum_w"], cs["n_observed"], cs["n_negative"]], np.float64)
     path = os.path.join(HERE, name + ".npz")

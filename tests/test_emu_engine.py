@@ -51,14 +51,14 @@ CASE = dict(scene=dict(color=True), vpb=8, vox_size=0.04, trunc=0.2, max_depth=3
 
 
 # kernel revisions (integrate, allocation, marching cubes): 0 = shipped defaults, 1 = opt-in (VH_INTEGRATE_REV / VH_ALLOC_REV / VH_MC_REV = 1)
-@pytest.mark.parametrize("rev,alloc_rev,mc_rev", [(1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (2, 0, 0), (2, 1, 1), (1, 2, 0), (2, 2, 1)])
+@pytest.mark.parametrize("rev,alloc_rev,mc_rev", [(1, 0, 0), (2, 0, 0), (1, 2, 0), (2, 2, 0)])
 def test_emulated_engine_matches_oracle(vh, ob, synth, rev, alloc_rev, mc_rev):
     nblocks, ntris = run_pair(vh, ob, synth, SMALL, CASE, frames=3, rev=rev, alloc_rev=alloc_rev, mc_rev=mc_rev, num_buckets=1 << 12,
                               pool_blocks=1 << 12, tri_arena_bytes=8 << 20)
     assert nblocks > 200 and ntris > 1000
 
 
-@pytest.mark.parametrize("alloc_rev", [0, 1, 2])
+@pytest.mark.parametrize("alloc_rev", [0, 2])
 def test_emulated_engine_negative_coordinates_no_colour(vh, ob, synth, alloc_rev):
     sc = dict(width=160, height=120, room=(4.0, 3.0, 2.5), room_min=(-2.0, -1.5, -1.25), n_frames=60, holes=0.02)
     case = dict(scene={}, vpb=8, vox_size=0.04, trunc=0.2, max_depth=3.0)
@@ -86,7 +86,7 @@ def test_emulated_engine_matches_reference_golden(name, vh, synth):
         assert np.array_equal(xyz, g["tri_xyz"]) and np.array_equal(trgb, g["tri_rgb"])
 
 
-@pytest.mark.parametrize("nranks,group,alloc_rev", [(2, 8, 0), (3, 1, 1), (2, 8, 2), (3, 1, 2), (4, 2, 2)])
+@pytest.mark.parametrize("nranks,group,alloc_rev", [(2, 8, 0), (3, 1, 0), (2, 8, 2), (3, 1, 2), (4, 2, 2)])
 def test_emulated_sharded_map_equals_single_map(vh, ob, synth, nranks, group, alloc_rev):
     """one map sharded by block-coordinate hash over N emulated ranks (ownership filter in the allocation kernel, remote
     table probes and halo reads in both marching-cubes kernels): the union is the oracle's single map, bit for bit"""
@@ -129,7 +129,7 @@ def test_emulated_sharded_map_equals_single_map(vh, ob, synth, nranks, group, al
         assert xyz.shape == xyz_o.shape and np.array_equal(xyz.view(np.uint32), xyz_o.view(np.uint32)) and np.array_equal(trgb, rgb_o)
 
 
-@pytest.mark.parametrize("alloc_rev", [0, 1, 2])
+@pytest.mark.parametrize("alloc_rev", [0, 2])
 def test_emulated_engine_other_launch_shapes(vh, ob, synth, alloc_rev):
     """non-default run-time values of the reference's macros: DDA stride 7, 160 ray steps (a larger dynamic shared-memory
     carve-out in the allocation kernel), unbounded chunk world, 16:9 image"""
@@ -171,7 +171,7 @@ def test_emulated_engine_pool_and_table_exhaustion_raise_flags(vh, synth):
         assert rc & 1, "MAP_TABLE_FULL not raised"
 
 
-@pytest.mark.parametrize("alloc_rev", [0, 1, 2])
+@pytest.mark.parametrize("alloc_rev", [0, 2])
 def test_emulated_allocation_dda_ties(vh, ob, synth, alloc_rev):
     """axis-aligned poses with the camera on block boundaries: for the pixels on the image diagonals two axes of the DDA
     cross block faces at exactly the same ray parameter, so the reference's tie rule decides which block is visited
@@ -240,7 +240,7 @@ def _random_pose_scene(synth, seed, **kw):
     return RandomPoses(**kw)
 
 
-@pytest.mark.parametrize("seed,revs", [(1, (1, 0, 0)), (2, (1, 1, 1)), (3, (2, 1, 1)), (4, (1, 0, 1)), (5, (2, 2, 0)), (6, (1, 2, 1))])
+@pytest.mark.parametrize("seed,revs", [(1, (1, 0, 0)), (2, (1, 2, 0)), (3, (2, 0, 0)), (4, (1, 0, 0)), (5, (2, 2, 0)), (6, (1, 2, 0))])
 def test_emulated_engine_random_rigid_poses(vh, ob, synth, seed, revs):
     """odd image size (not a multiple of the 16-pixel tiles or the 10-pixel ray stride), off-centre principal point,
     random rigid poses; three frames that overlap only by chance"""
@@ -266,7 +266,7 @@ def test_emulated_engine_random_rigid_poses(vh, ob, synth, seed, revs):
         assert len(keys) > 100
 
 
-@pytest.mark.parametrize("mc_rev", [0, 1])
+@pytest.mark.parametrize("mc_rev", [0])
 def test_emulated_full_map_extraction(vh, ob, synth, mc_rev):
     """VH_MESH_FULL_MAP: every allocated block re-meshed against the whole map (a corner counts if its block is allocated at
     all) — list_all_blocks_kernel + both marching-cubes kernels with full_map = 1 — against the oracle's full-map pass;
@@ -302,6 +302,6 @@ def test_emulated_engine_under_another_thread_order():
     for order in ("reverse", "random:3"):
         env = dict(os.environ, VH_EMU_ORDER=order, VH_EMU_NO_REBUILD="1")
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_engine.py"), "-x", "-q", "-p", "no:cacheprovider",
-                            "-k", "matches_oracle and 2-2-1 or sharded and 3-1-2 or merge_equals"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+                            "-k", "matches_oracle and 2-2-0 or sharded and 3-1-2 or merge_equals"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
         assert r.returncode == 0, f"VH_EMU_ORDER={order}:\n{r.stdout[-2000:]}"
         assert "3 passed" in r.stdout, r.stdout[-500:]

@@ -1,6 +1,6 @@
-"""GPU (B200): alloc_visible_kernel_r1 (VH_ALLOC_REV=1: the 3-D DDA as a three-way merge instead of a sequential march)
-through the C ABI against the goldens and the oracle. Opt-in and, when written, checked under CPU emulation only
-(tests/test_emu_engine.py) — runs with VH_TEST_REV1=1 (tools/gpu_rev1.sh), see tests/test_gpu_integrate_rev1.py."""
+"""GPU (B200): both allocation forms — the one-kernel alloc_visible_kernel (VH_ALLOC_REV=0, default at the reference's 100-step ray
+cap on one GPU) and ray_keys_kernel + insert_keys_kernel (VH_ALLOC_REV=2: the DDA as a three-way merge, keys through an inbox;
+default for sharded maps and long ray caps) — through the C ABI against the goldens and the oracle."""
 import os
 
 import pytest
@@ -11,14 +11,13 @@ from util import CASES, engine_params, key_set, load_golden, oracle_params
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["0", "1"], ids=["integrate0", "integrate1"])
+@pytest.fixture(params=["0", "2"], ids=["one-kernel", "keys+insert"])
 def alloc1(request, monkeypatch):
-    monkeypatch.setenv("VH_ALLOC_REV", "1")
-    monkeypatch.setenv("VH_INTEGRATE_REV", request.param)
+    monkeypatch.setenv("VH_ALLOC_REV", request.param)
 
 
 @pytest.mark.parametrize("name", ["g8_color_holes", "g8_negative_coords"])
-def test_alloc_rev1_matches_reference_golden(name, vh, synth, alloc1):
+def test_alloc_matches_reference_golden(name, vh, synth, alloc1):
     case, g = CASES[name], load_golden(name)
     sc = synth.Scene(**case["scene"])
     color = bool(case["scene"].get("color"))
@@ -31,13 +30,13 @@ def test_alloc_rev1_matches_reference_golden(name, vh, synth, alloc1):
         assert_triangles_match(*eng.triangles(), g["tri_xyz"], g["tri_rgb"], color)
 
 
-def test_alloc_rev1_headline_sequence(vh, ob, synth, alloc1):
+def test_alloc_headline_sequence(vh, ob, synth, alloc1):
     sc = synth.make_scene("C2", color=True)
     case = dict(scene=dict(color=True), vpb=8, vox_size=0.005, trunc=0.025, max_depth=10.0)
     run_pair(vh, ob, sc, case, frames=24, num_buckets=1 << 20, pool_blocks=1 << 19, tri_arena_bytes=2 << 30)
 
 
-def test_alloc_rev1_1cm_and_long_rays(vh, ob, synth, alloc1):
+def test_alloc_1cm_and_long_rays(vh, ob, synth, alloc1):
     sc = synth.make_scene("C1")
     case = dict(scene={}, vpb=8, vox_size=0.01, trunc=0.05, max_depth=10.0)
     run_pair(vh, ob, sc, case, frames=4, num_buckets=1 << 20, pool_blocks=1 << 19, tri_arena_bytes=512 << 20)

@@ -1,9 +1,5 @@
-"""GPU (B200): integrate_kernel_r1 (VH_INTEGRATE_REV=1) through the C ABI against the goldens and the oracle.
-
-The revision is opt-in and, when this file was written, had only been checked under CPU emulation
-(tests/test_emu_integrate.py) — the round's GPU budget was spent. The tests therefore run only with VH_TEST_REV1=1
-(tools/gpu_rev1.sh sets it); once they have passed on a B200 the revision can become the default and the gate can go.
-"""
+"""GPU (B200): both integrate kernels (integrate_kernel_staged: planes through shared memory by bulk async copies, the default;
+integrate_kernel_direct: per-lane plane loads) at their launch shapes, through the C ABI against the goldens and the oracle."""
 import os
 
 import numpy as np
@@ -15,18 +11,17 @@ from util import CASES, engine_params, load_golden
 pytestmark = pytest.mark.gpu
 
 
-# (revision, CTAs per SM, steps gated together): revision 1 = per-lane plane loads after the gate; revision 2 = planes staged in
-# shared memory by bulk async copies (cp.async.bulk + mbarrier)
-@pytest.fixture(params=[("1", "3", "0"), ("1", "4", "0"), ("2", "4", "1"), ("2", "4", "0"), ("2", "3", "1")],
-                ids=["r1-3ctas", "r1-4ctas", "r2-4ctas-2steps", "r2-4ctas-1step", "r2-3ctas-2steps"])
-def rev1(request, monkeypatch):
+# (VH_INTEGRATE_REV, CTAs per SM, steps gated together): 1 = direct (per-lane plane loads after the gate), 2 = staged (cp.async.bulk + mbarrier)
+@pytest.fixture(params=[("2", "4", "1"), ("2", "6", "0"), ("2", "5", "1"), ("1", "3", "0"), ("1", "4", "0")],
+                ids=["staged-4ctas-2steps", "staged-6ctas-1step", "staged-5ctas-2steps", "direct-3ctas", "direct-4ctas"])
+def kernel(request, monkeypatch):
     monkeypatch.setenv("VH_INTEGRATE_REV", request.param[0])
     monkeypatch.setenv("VH_INTEGRATE_CTAS", request.param[1])
     monkeypatch.setenv("VH_INTEGRATE_TWO_STEPS", request.param[2])
 
 
 @pytest.mark.parametrize("name", ["g8_color_holes", "g8_negative_coords"])
-def test_rev1_matches_reference_golden(name, vh, synth, rev1):
+def test_integrate_matches_reference_golden(name, vh, synth, kernel):
     case, g = CASES[name], load_golden(name)
     sc = synth.Scene(**case["scene"])
     color = bool(case["scene"].get("color"))
@@ -39,7 +34,7 @@ def test_rev1_matches_reference_golden(name, vh, synth, rev1):
         assert cs["sum_w"] == g["checksum"][1] and cs["n_observed"] == g["checksum"][2] and cs["n_negative"] == g["checksum"][3]
 
 
-def test_rev1_general_colour_path(vh, synth, rev1, monkeypatch):
+def test_integrate_general_colour_path(vh, synth, kernel, monkeypatch):
     monkeypatch.setenv("VH_INTEGRATE_EXACT_COLOR", "1")     # weights "above 65536": the general division sequence
     name = "g8_color_holes"
     case, g = CASES[name], load_golden(name)
@@ -50,14 +45,14 @@ def test_rev1_general_colour_path(vh, synth, rev1, monkeypatch):
         assert_voxels_match(eng, g["keys"], g["sdf"], g["weight"], g["rgb"], True)
 
 
-def test_rev1_headline_sequence(vh, ob, synth, rev1):
+def test_integrate_headline_sequence(vh, ob, synth, kernel):
     """40 frames of BASELINE config 2 (the bench workload): per-frame counters, every voxel, the ordered mesh."""
     sc = synth.make_scene("C2", color=True)
     case = dict(scene=dict(color=True), vpb=8, vox_size=0.005, trunc=0.025, max_depth=10.0)
     run_pair(vh, ob, sc, case, frames=40, num_buckets=1 << 20, pool_blocks=1 << 19, tri_arena_bytes=2 << 30)
 
 
-def test_rev1_revisits_and_hostile_depth(vh, ob, synth, rev1):
+def test_integrate_revisits_and_hostile_depth(vh, ob, synth, kernel):
     """weights > 1 and NaN / inf / negative / denormal depth samples (the out-of-line IEEE redo of a step)"""
     sc = synth.Scene(width=320, height=240, room=(5.0, 4.0, 2.6), n_frames=40, spheres=((3.9, 2.0, 1.0, 0.5),), color=True)
     case = dict(scene=dict(color=True), vpb=8, vox_size=0.02, trunc=0.1, max_depth=3.5)
@@ -80,7 +75,7 @@ def test_rev1_revisits_and_hostile_depth(vh, ob, synth, rev1):
         assert np.array_equal(c2, rgb_)
 
 
-def test_rev1_verify_mode_counts_no_disagreement(vh, synth, rev1, monkeypatch):
+def test_integrate_verify_mode_counts_no_disagreement(vh, synth, kernel, monkeypatch):
     """VH_INTEGRATE_VERIFY=1: fast and IEEE formulations side by side inside the kernel, zero disagreements"""
     monkeypatch.setenv("VH_INTEGRATE_VERIFY", "1")
     sc = synth.make_scene("C2", color=True)

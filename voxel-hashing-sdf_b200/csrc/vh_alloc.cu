@@ -198,23 +198,22 @@ alloc_visible_kernel(const StaticParams S, const FrameParams F, const float* __r
 }
 
 // ======================================================================================================================
-// Revision 1 (opt-in: VH_ALLOC_REV=1). Same rays, same visited blocks, same insertion code — but the 3-D DDA is no
-// longer marched step by step. The reference's loop (tsdf.cu:2158-2233) keeps one crossing time per axis and advances
-// the axis with the smallest one, adding that axis's increment by repeated float addition. The k-th crossing time of an
-// axis therefore does not depend on the other axes: T_a[k] = tmax_a + tdel_a + ... (k additions) is a monotone sequence
-// that one lane can generate alone (24 lanes: 8 rays x 3 axes, a chain of K dependent FADDs each), and the loop's choice
+// The 3-D DDA as a MERGE (used by ray_keys_kernel below). The reference's loop (tsdf.cu:2158-2233) keeps one crossing time per
+// axis and advances the axis with the smallest one, adding that axis's increment by repeated float addition. The k-th crossing
+// time of an axis therefore does not depend on the other axes: T_a[k] = tmax_a + tdel_a + ... (k additions) is a monotone
+// sequence that one lane can generate alone (a chain of K dependent FADDs, bit-identical to the reference's accumulation), and
+// the loop's choice
 //     x if tx < ty && tx < tz;  else z if tz < ty;  else y
 // is "take the smallest head, ties resolved y before z before x" — a three-way MERGE of the sequences under the total
 // order (time, priority). Every element then finds its own place: element k of axis a is step
 //     pos = k + #{elements of b before it} + #{elements of c before it}
-// with the two counts taken by binary search, and those same counts are how far the ray has moved along b and c when it
-// takes that step — so the block visited at step pos is (cur0_a + k*step_a, cur0_b + n_b*step_b, cur0_c + n_c*step_c). The
-// ray ends at the first step that carries a coordinate onto its bound (an atomicMin over the three candidates). The
-// sequential march (~40 dependent instructions per step, 100 steps, ~20 us) becomes ~2 us of parallel work, and all of
-// the CTA's keys are classified and inserted in rounds of 256 instead of 200 behind a marching warp.
-// Non-finite crossing times (a pose with NaNs) cannot index out of range: positions are checked, unwritten steps stay empty.
-// Shared memory: 160 B per step of the cap (16 KB at the reference's 100 steps; 172 KB at the 1,100 of the room-scale config).
-constexpr int ALLOC1_MAX_SMEM = 224 * 1024;      // of the 227 KB a CTA can have: step caps up to ~1,400
+// and those same counts are how far the ray has moved along b and c when it takes that step — so the block visited at step
+// pos is (cur0_a + k*step_a, cur0_b + n_b*step_b, cur0_c + n_c*step_c). The ray ends at the first step that carries a
+// coordinate onto its bound (an atomicMin over the three candidates). The sequential march (~40 dependent instructions per
+// step) becomes parallel work over (ray, axis, k). Non-finite crossing times (a pose with NaNs) cannot index out of range:
+// positions are checked, unwritten steps stay empty. Under CPU emulation the merge equals the step-by-step DDA key by key, exact
+// ties between axes included (tests/test_emu_engine.py); on B200 it reproduces the oracle's visible sets on every config.
+constexpr int ALLOC1_MAX_SMEM = 224 * 1024;      // of the 227 KB a CTA can have: ray_keys_kernel's smallest tile (2 rays, 40 B per step) handles step caps up to ~5,700
 
 __device__ __forceinline__ int axis_priority(int a) { return a == 1 ? 0 : (a == 2 ? 1 : 2); }   // ties: y, then z, then x
 
@@ -244,143 +243,14 @@ __device__ __forceinline__ int merge_rank_near(const float* __restrict__ t, int 
   return merge_rank(t, n, v, ties_first);
 }
 
-// phases 0-2 for the CTA's tile of rays: skeys[step * RAYS + ray] = block visited at that step (KEY_EMPTY where the block is
-// outside the key range), s_death[ray] = last step the ray takes (K if it never reaches a bound). All threads of the CTA.
-__device__ __forceinline__ void merge_fill_keys(const StaticParams& S, const FrameParams& F, const float* __restrict__ depth, int tile_x, int tile_y,
-                                                u64* __restrict__ skeys, float* __restrict__ sT, int* __restrict__ s_death) {
-  __shared__ int s_cur[RAYS][3], s_step[RAYS][3], s_last[RAYS][3], s_alive[RAYS];
-  __shared__ float s_del[RAYS][3], s_inv[RAYS][3];
-  const int K = S.max_steps;
-  const int tid = threadIdx.x;
-
-  // phase 0: ray set-up (8 lanes), every step slot empty
-  if (tid < RAYS) {
-    RayState R;
-    ray_setup(S, F, depth, tile_x * RAYS_X + (tid & (RAYS_X - 1)), tile_y * RAYS_Y + (tid / RAYS_X), R);
-    s_alive[tid] = R.alive ? 1 : 0;
-    s_death[tid] = K;                                                 // no step ends the ray (yet)
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      s_cur[tid][a] = R.cur[a]; s_step[tid][a] = R.istep[a];
-      // the a-step that carries cur_a onto bound_a is number (bound - cur) / step, counted from 1; none if the bound is not ahead
-      const long long ahead = ((long long)R.bound[a] - (long long)R.cur[a]) * (long long)R.istep[a];
-      s_last[tid][a] = (R.istep[a] != 0 && ahead >= 1 && ahead <= (long long)K) ? (int)ahead - 1 : -1;
-      sT[(tid * 3 + a) * K] = R.tmax[a];
-      s_del[tid][a] = R.tdel[a];
-      s_inv[tid][a] = R.tdel[a] > 0.0f ? fdiv(1.0f, R.tdel[a]) : 0.0f;         // estimate only (merge_rank_near); +inf -> 0
-    }
-  }
-  for (int i = tid; i < K * RAYS; i += (int)blockDim.x) skeys[i] = KEY_EMPTY;
-  __syncthreads();
-
-  // phase 1: the crossing times of every axis by repeated addition (tsdf.cu:2221,2226,2231), one lane per (ray, axis)
-  if (tid < RAYS * 3) {
-    float* t = sT + (size_t)tid * K;
-    float v = t[0];
-    const float del = s_del[tid / 3][tid % 3];
-    for (int k = 1; k < K; k++) { v = fadd(v, del); t[k] = v; }
-  }
-  __syncthreads();
-
-  // phase 2: every element finds its step and the block the ray is in when it takes it. A warp takes (ray, axis) pairs,
-  // its lanes the elements k of the pair; an element whose step is already beyond the cap after the first count is dropped.
-  const int nwarps = (int)blockDim.x >> 5, wid = tid >> 5, lane = tid & 31;
-  for (int ra = wid; ra < RAYS * 3; ra += nwarps) {
-    const int ray = ra / 3, a = ra - ray * 3;
-    if (!s_alive[ray]) continue;
-    const int b = a == 0 ? 1 : 0, c = a == 2 ? 1 : 2;                 // the other two axes
-    const int pa = axis_priority(a);
-    const bool tb = axis_priority(b) < pa, tc = axis_priority(c) < pa;
-    const float* Ta = sT + (size_t)ra * K;
-    const float* Tb = sT + (size_t)(ray * 3 + b) * K;
-    const float* Tc = sT + (size_t)(ray * 3 + c) * K;
-    const float ib = s_inv[ray][b], ic = s_inv[ray][c];
-    for (int k = lane; k < K; k += 32) {
-      const float v = Ta[k];
-      const int nb = merge_rank_near(Tb, K, v, tb, ib);
-      if (k + nb >= K) continue;
-      const int nc = merge_rank_near(Tc, K, v, tc, ic);
-      const int pos = k + nb + nc;
-      if (pos < 0 || pos >= K) continue;
-      int cur[3];
-      cur[a] = s_cur[ray][a] + k * s_step[ray][a]; cur[b] = s_cur[ray][b] + nb * s_step[ray][b]; cur[c] = s_cur[ray][c] + nc * s_step[ray][c];
-      if (key_in_range(cur[0], cur[1], cur[2])) skeys[pos * RAYS + ray] = pack_key(cur[0], cur[1], cur[2]);
-      if (k == s_last[ray][a]) atomicMin(&s_death[ray], pos);         // this step moves the ray onto its bound (tsdf.cu:2219,2224,2229)
-    }
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(ALLOC_THREADS)
-alloc_visible_kernel_r1(const StaticParams S, const FrameParams F, const float* __restrict__ depth, const DeviceView D, int tiles_x) {
-#ifdef VH_HOST_EMU
-  u64* dyn = reinterpret_cast<u64*>(emu::g_cta->dyn_smem);
-#else
-  extern __shared__ u64 dyn[];
-#endif
-  const int K = S.max_steps;
-  u64* skeys = dyn;                                                   // [K][RAYS]
-  float* sT = reinterpret_cast<float*>(dyn + (size_t)K * RAYS);       // [RAYS][3][K] crossing times
-  int* s_first = reinterpret_cast<int*>(sT);                          // [K * RAYS] entries first seen this frame: reuses the crossing times, dead after phase 2
-  __shared__ int s_death[RAYS];
-  __shared__ int s_cnt, s_base;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-  if (tid == 0) s_cnt = 0;
-  merge_fill_keys(S, F, depth, tile_x, tile_y, skeys, sT, s_death);
-
-  // phase 3: classify, insert, stamp and collect — the code of alloc_visible_kernel, over all K x RAYS keys
-  const float bpc = (float)S.bpc;
-  const int nkeys = K * RAYS;
-  for (int i0 = 0; i0 < nkeys; i0 += ALLOC_THREADS) {
-    const int i = i0 + tid;
-    u64 key = KEY_EMPTY;
-    if (i < nkeys && i / RAYS <= s_death[i % RAYS]) key = skeys[i];
-    if (key != KEY_EMPTY) {
-      int bx, by, bz;
-      unpack_key(key, bx, by, bz);
-      // sharded map: the (cheap) ownership test first, so that a rank spends the two geometric tests on its own blocks only
-      bool ok = S.shard_count <= 1 || owner_of_block(bx, by, bz, S.shard_count, S.shard_group) == S.shard_rank;
-      if (ok) ok = chunk_is_candidate(S, F, block_to_chunk(bx, bpc), block_to_chunk(by, bpc), block_to_chunk(bz, bpc));   // tsdf.cu:2164
-      if (ok) ok = block_in_frustum(S, F, bx, by, bz);                                                                  // tsdf.cu:2165
-      if (!ok) key = KEY_EMPTY;
-    }
-    if (__ballot_sync(0xffffffffu, key != KEY_EMPTY) != 0) {
-      const unsigned same = __match_any_sync(0xffffffffu, key);
-      const bool leader = key != KEY_EMPTY && lane == __ffs(same) - 1;
-      int entry = -1;
-      bool claimed = false;
-      if (leader) entry = map_claim(D.map, key, claimed);
-      map_assign_slots(D.map, 0xffffffffu, claimed, entry, key);
-      bool first = false;
-      if (leader && entry >= 0) first = atomicExch(&D.stamps[entry], F.frame) != F.frame;
-      const unsigned fm = __ballot_sync(0xffffffffu, first);
-      if (fm) {
-        const int l0 = __ffs(fm) - 1;
-        int base = 0;
-        if (lane == l0) base = atomicAdd(&s_cnt, __popc(fm));
-        base = __shfl_sync(0xffffffffu, base, l0);
-        if (first) s_first[base + __popc(fm & ((1u << lane) - 1))] = entry;
-      }
-    }
-  }
-  __syncthreads();
-  const int cnt = s_cnt;
-  if (cnt == 0) return;
-  if (tid == 0) s_base = atomicAdd(&D.counters->visible_count, cnt);
-  __syncthreads();
-  const int base = s_base;
-  for (int i = tid; i < cnt; i += ALLOC_THREADS)
-    if (base + i < D.list_cap) D.visible[base + i] = s_first[i];
-}
-
 // ======================================================================================================================
-// Revision 2: allocation as TWO kernels with a key list in between — ray_keys_kernel -> (inbox) -> insert_keys_kernel.
-// The one-kernel forms above interleave a few thousand DDA steps with hash-table insertions inside every CTA: each round of
+// Allocation as TWO kernels with a key list in between — ray_keys_kernel -> (inbox) -> insert_keys_kernel (alloc_rev 2: sharded maps
+// and long ray step caps; the one-kernel form above stays the default for the reference's 100-step cap on one GPU, where it is
+// ~5 us faster: profiles/r02e). The one-kernel form interleaves a few thousand DDA steps with hash-table insertions inside every CTA: each round of
 // 256 keys walks a chain of dependent global accesses (probe -> CAS -> pool pop -> stamp exchange -> list append) with at most
 // 20 warps per SM to hide it (profiles/r02b: 24 us, issue slots 28 % busy, barrier + long-scoreboard stalls), and at the
 // 1,100-step cap of the room-scale config that chain repeats 34 times per CTA (0.40 ms). Split in two:
-//   ray_keys_kernel    the merge formulation of the DDA (see alloc_visible_kernel_r1) for a tile of TRX x TRY rays, then every key of
+//   ray_keys_kernel    the merge formulation of the DDA (above) for a tile of TRX x TRY rays, then every key of
 //                      the tile is classified (ray end, chunk candidate test, frustum test) — pure arithmetic, no global access — and
 //                      the survivors are appended to the INBOX of the GPU that owns the block: one reservation per owner per CTA.
 //                      On a single GPU the owner is this GPU; on a sharded map the inbox of a peer is written over NVLink (stores
@@ -551,16 +421,17 @@ insert_keys_kernel(const __grid_constant__ DeviceView D, const uint32_t frame) {
       for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ci, o), v = __shfl_up_sync(0xffffffffu, fi, o); if (lane >= o) { ci += u; fi += v; } }
       if (lane < INSERT_THREADS / 32) { s_wclaim[lane] = ci - c; s_wfirst[lane] = fi - f; }
       const int nc = __shfl_sync(0xffffffffu, ci, 31), nf = __shfl_sync(0xffffffffu, fi, 31);
-      if (lane == 0) {
-        int top = 0, heap = 0, vis = 0;
+      if (lane == 0) {          // pool pop, then the key_heap reservation for what was granted
+        int top = 0, heap = 0;
         if (nc > 0) {
           top = atomicSub(D.map.free_top, nc);
           const int granted = top >= nc ? nc : (top > 0 ? top : 0);
           if (granted < nc) atomicAdd(D.map.free_top, nc - granted);          // pool exhausted: hand back the share that was not there
           if (granted > 0) heap = atomicAdd(D.map.heap_counter, granted);
         }
-        if (nf > 0) vis = atomicAdd(&D.counters->visible_count, nf);
-        s_top = top; s_heap = heap; s_vis = vis;
+        s_top = top; s_heap = heap;
+      } else if (lane == 1) {   // the visible-list reservation travels at the same time
+        s_vis = nf > 0 ? atomicAdd(&D.counters->visible_count, nf) : 0;
       }
     }
     __syncthreads();
@@ -587,10 +458,6 @@ insert_keys_kernel(const __grid_constant__ DeviceView D, const uint32_t frame) {
     __threadfence();
     if (atomicAdd(&D.inbox_done[parity], 1) == (int)gridDim.x - 1) { D.inbox_count[parity] = 0; D.inbox_done[parity] = 0; __threadfence(); }
   }
-}
-
-inline size_t alloc_r1_smem_bytes(int max_steps) {
-  return (size_t)max_steps * RAYS * sizeof(u64) + (size_t)RAYS * 3 * max_steps * sizeof(float);     // keys + crossing times (160 B per step)
 }
 
 #ifndef VH_HOST_EMU
@@ -626,12 +493,6 @@ void launch_alloc_visible(const StaticParams& S, const FrameParams& F, const flo
     return;
   }
   const int tiles_x = (S.nrx + RAYS_X - 1) / RAYS_X, tiles_y = (S.nry + RAYS_Y - 1) / RAYS_Y;
-  if (S.alloc_rev == 1 && alloc_r1_smem_bytes(S.max_steps) <= (size_t)ALLOC1_MAX_SMEM) {      // opt-in revision, see alloc_visible_kernel_r1
-    const size_t smem1 = alloc_r1_smem_bytes(S.max_steps);
-    if (smem1 > 48 * 1024) cudaFuncSetAttribute(alloc_visible_kernel_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    alloc_visible_kernel_r1<<<tiles_x * tiles_y, ALLOC_THREADS, smem1, st>>>(S, F, d_depth, D, tiles_x);
-    return;
-  }
   const size_t smem = 2 * CHUNK_KEYS * sizeof(u64) + (size_t)S.max_steps * RAYS * sizeof(int);
   if (smem > 48 * 1024)   // per-device attribute; only very long ray step caps get here
     cudaFuncSetAttribute(alloc_visible_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -144,12 +144,16 @@ int vh_create(const vh_params* p, vh_engine** out) {
   StaticParams& S = e->S;
   derive_static_params(*p, S);
   { const char* v = getenv("VH_INTEGRATE_VERIFY"); S.verify = (v && v[0] == '1') ? 1 : 0; }
-  { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && (v[0] == '3' || v[0] == '4')) ? v[0] - '0' : 0; }   // tuning knob; 0 = the kernel's default (direct 3, staged 4)
+  { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '3' && v[0] <= '6') ? v[0] - '0' : 0; }   // tuning knob; 0 = the kernel's default (direct 3 [or 4], staged 4 [or 5, 6])
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_env = e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '0') ? 0 : 1; }
   { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] == '1') ? 1 : 2; }      // 2 (default) = integrate_kernel_staged, 1 = integrate_kernel_direct
-  { const char* v = getenv("VH_ALLOC_REV"); S.alloc_rev = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 0; }
+  { // allocation: 2 = ray_keys_kernel + insert_keys_kernel (sharded maps: rays split across the GPUs; long ray step caps), 0 = the one-kernel
+    // form (a few us faster at the reference's 100-step cap on one GPU); VH_ALLOC_REV overrides
+    const char* v = getenv("VH_ALLOC_REV");
+    S.alloc_rev = (v && (v[0] == '0' || v[0] == '2')) ? v[0] - '0' : ((p->shard_count > 1 || p->max_ray_steps > 256) ? 2 : 0);
+  }
   S.mc_rev = 0;      // (unused: the marching-cubes revisions of round 1 were measured and merged)
   static_assert(sizeof(StaticParams) % 16 == 0, "keep the FrameParams behind StaticParams 16-byte aligned in the kernels' parameter blocks");
 

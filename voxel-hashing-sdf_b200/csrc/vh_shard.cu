@@ -7,9 +7,9 @@
 //   * vh_integrate_sharded / vh_integrate_sharded_device, per frame (collective, same order on every rank):
 //       rank 0 puts {pose, depth, rgb} into a slot of its frame ring (H2D from the caller's host buffers on the upload stream,
 //       double-buffered, or one device copy) and raises a sequence flag in every peer's memory;
-//       every GPU's pack_frame_kernel READS THE FRAME OUT OF RANK 0'S MEMORY OVER NVLINK while packing it — broadcast and
-//       first compute step are one kernel, there is no staging copy and no collective launch (VH_SHARD_BCAST=nccl selects the
-//       ncclBroadcast of round 1 instead, kept as the baseline: it costs a ~100 us serial chain per frame);
+//       every other GPU's upload stream waits for the flag and PULLS the frame out of rank 0's ring over NVLink with one copy-engine
+//       transfer into its own ring, one frame ahead of its compute stream: no collective launch, no SM time (VH_SHARD_BCAST=nccl
+//       selects a per-frame ncclBroadcast instead, kept as the baseline);
 //       ray_keys_kernel: the rays are SPLIT across the GPUs; every key goes to its owner's inbox with NVLink stores;
 //       frame barrier; insert_keys_kernel on the own inbox; work list; integrate of the own blocks;
 //       second barrier; marching cubes — neighbour blocks are looked up in the table of the GPU their key hashes to and
@@ -291,7 +291,7 @@ static int integrate_sharded_common(vh_engine* e, const float* depth, const uint
   // Rank 0 fills the slot on its upload stream, double-buffered: frame k+1 arrives over PCIe while frame k is being integrated and
   // meshed. The slot's previous frame (k-1) is no longer read once every GPU is past frame k-1's barrier (`released`).
   cudaStream_t up = e->upload;
-  if (s->rank == 0 || !s->pull) { if (s->used[b]) CK(cudaStreamWaitEvent(up, s->pull ? s->released[b] : s->consumed[b], 0)); }
+  if (s->used[b]) CK(cudaStreamWaitEvent(up, (s->pull && s->rank == 0) ? s->released[b] : s->consumed[b], 0));
   if (s->rank == 0) {
     uint8_t* hbuf = s->h_frame + (size_t)b * s->frame_bytes;
     if (s->used[b]) CK(cudaEventSynchronize(s->uploaded[b]));    // staging slot b's previous upload (two frames ago) has left the host
@@ -322,15 +322,21 @@ static int integrate_sharded_common(vh_engine* e, const float* depth, const uint
       frame_ready_kernel<<<1, 32, 0, up>>>(fp, s->count, seq);
     }
   }
-  const uint8_t* src = s->pull ? s->frame_src + (size_t)b * s->frame_bytes : dbuf;
+  // Every other GPU fetches the frame on ITS upload stream — a spin on the sequence flag, then one copy-engine transfer out of rank 0's
+  // ring over NVLink into the own ring — so frame k+1 arrives while frame k is being integrated and meshed: no collective launch, no
+  // SM time, nothing on the compute stream's critical path (kernels reading rank 0's memory in place were measured at 8 GPUs:
+  // the pack kernel's small loads over NVLink cost ~50 us per frame, profiles/r02g). VH_SHARD_BCAST=nccl: ncclBroadcast instead.
+  const uint8_t* src = dbuf;
   if (s->pull) {
-    if (s->rank == 0) { CK(cudaEventRecord(s->arrived[b], up)); CK(cudaStreamWaitEvent(e->stream, s->arrived[b], 0)); }
-    else frame_wait_kernel<<<1, 32, 0, e->stream>>>(s->d_flags, seq, e->D.engine_error);
+    if (s->rank != 0) {
+      frame_wait_kernel<<<1, 32, 0, up>>>(s->d_flags, seq, e->D.engine_error);
+      CK(cudaMemcpyAsync(dbuf, s->frame_src + (size_t)b * s->frame_bytes, bytes, cudaMemcpyDefault, up));
+    }
   } else {
     NK(g_nccl.Broadcast(dbuf, dbuf, bytes, ncclChar, 0, s->comm, up));
-    CK(cudaEventRecord(s->arrived[b], up));
-    CK(cudaStreamWaitEvent(e->stream, s->arrived[b], 0));
   }
+  CK(cudaEventRecord(s->arrived[b], up));
+  CK(cudaStreamWaitEvent(e->stream, s->arrived[b], 0));
   CK(cudaEventRecord(e->ev[1], e->stream));
   float pose[16];
   if (c2w) memcpy(pose, c2w, sizeof(pose));
@@ -339,7 +345,7 @@ static int integrate_sharded_common(vh_engine* e, const float* depth, const uint
     CK(cudaStreamSynchronize(e->stream));
     memcpy(pose, s->h_pose, sizeof(pose));
   }
-  e->cur_depth = reinterpret_cast<const float*>(src + 64);                      // rank 0's memory in pull mode: read over NVLink by the kernels below
+  e->cur_depth = reinterpret_cast<const float*>(src + 64);
   e->cur_rgb = with_rgb ? src + 64 + npx * 4 : nullptr;
   setup_frame(e, pose);
   DeviceView& D = e->D;
