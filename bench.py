@@ -87,6 +87,8 @@ def config_dict(args, cfg, sc, world):
                     f"{cfg['vox_size'] * 1000:g} mm voxels, 8^3 blocks, {cfg['num_buckets']}-bucket x4 hash, trunc {cfg['trunc'] * 100:g} cm, MaxDepth {cfg['max_depth']:g}",
         "max_ray_steps": args.ray_steps or 100,
         "frames_per_step": FRAMES_PER_STEP,
+        "sequence_replay": (f"{args.steps} steps x {FRAMES_PER_STEP} frames = {args.steps * FRAMES_PER_STEP} frames over a {frame_cap(args, sc)}-frame sequence: "
+                            + ("the sequence is replayed; later passes revisit the map of the first (no new blocks, weights keep growing)" if args.steps * FRAMES_PER_STEP > frame_cap(args, sc) else "one pass from an empty map")),
         "per_frame_path": "upload + allocate + integrate" + ("" if args.no_mc else " + working-set marching cubes"),
         "color": not args.no_color,
         "multi_gpu": "one independent sequence+map per GPU (config 5 style), no collective on the data path" if world > 1 else "single map",
@@ -406,10 +408,15 @@ def run_ours(args):
             f.write("frame,ms_integrate,voxel_updates,visible_blocks,blocks_discarded,ms_alloc,ms_mc,triangles,ms_cull\n")
             for r in per_frame_rows:
                 f.write(",".join(str(x) for x in r) + "\n")
-    traffic, traffic_src = None, None
+    # DRAM traffic of ONE named launch (ncu --set full capture committed under profiles/) next to the algorithmic bytes of the SAME launch
+    traffic, traffic_src, traffic_alg = None, None, None
     tpath = os.path.join(ROOT, "profiles", "integrate_traffic.json")
     if os.path.exists(tpath) and args.config == "C2" and color:
         tj = json.load(open(tpath)); traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        fr_i = int(tj.get("sequence_frame", -1))
+        row = next((r for r in per_frame_rows if r[0] == fr_i), None)
+        if row is not None:
+            traffic_alg = 16.0 * row[2] + 4.0 * W * H + 12.0 * row[3] + 8.0 * row[2] + 3.0 * W * H
 
     h2d = W * H * 4 + (W * H * 3 if color else 0) + 64
     d2h = 104
@@ -432,9 +439,10 @@ def run_ours(args):
                       "arena_compactions_in_500_frames": int(st_last.arena_compactions)},
         "roofline": {"kernel": "vh::integrate_kernel_staged" if os.environ.get("VH_INTEGRATE_REV") == "2" else "vh::integrate_kernel_direct", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int, "frac_per_frame": frac_frames},
-        "roofline_mc": {"kernel": "vh::mc_filter_kernel + vh::mc_mesh_kernel", "bound": "hbm", "achieved": (bytes_mc / (ms_mc * 1e-3) / 1e9) if ms_mc > 0 else 0.0,
-                        "peak": peak, "unit": "GB/s", "algorithmic_bytes_per_launch": bytes_mc, "avg_launch_ms": ms_mc},
+                     "traffic_launch_algorithmic_bytes": traffic_alg, "algorithmic_bytes_per_launch": bytes_int, "avg_launch_ms": ms_int, "frac_per_frame": frac_frames},
+        "marching_cubes": {"kernels": "vh::mc_filter_kernel + vh::mc_mesh_kernel", "avg_ms_per_frame": ms_mc, "triangles_per_frame": tris_per_frame,
+                           "dram_bytes_per_frame_ncu": 31.3e6, "dram_source": "profiles/r02_ncu/ncu_full_mcfilter.txt + ncu_full_mcmesh.txt (23.6 MB + 7.7 MB read; the triangle writes stay in L2)",
+                           "note": "latency-bound chains of look-ups; the sign filter keeps the kernels from reading most of the working set, so an algorithmic-bytes/time figure would overstate bandwidth use: the statement is time"},
         "clocks": clocks,
         "export": export,
     }
@@ -572,12 +580,12 @@ def single_gpu_run(vh, torch, np, cfg_name, cfg, sc, color, mc, local, n_warm, n
             "integrate_roofline_frac": (bytes_int / (ms_int * 1e-3) / 1e9 / peak) if ms_int > 0 else None}
 
 
-def sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_warm, n_timed, ray_steps, pool_blocks, frames, host_inputs):
+def sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_warm, n_timed, ray_steps, pool_blocks, frames, with_host_inputs=True):
     """ONE map sharded over the GPUs by block hash on rank 0's sequence (north_star's multi-GPU path): per frame rank 0 puts
-    the frame into its ring (device copy, or H2D from pinned host buffers when host_inputs), every GPU packs it out of rank 0's
-    memory over NVLink, marches its share of the rays, sends block keys to their owners, integrates and meshes its own blocks.
-    Strong scaling: the work is fixed. Device time = max over ranks of the CUDA-event time on the engine's stream (and of the wall
-    clock of the enqueue loop, whichever is larger)."""
+    the frame into its ring (device copy, or H2D from pinned host buffers for the e2e figure), every other GPU's copy engine pulls it
+    over NVLink one frame ahead, every GPU marches its share of the rays, sends block keys to their owners, integrates and meshes its
+    own blocks. Strong scaling: the work is fixed. Time = max over ranks of the CUDA-event time on the engine's stream (and of the
+    wall clock of the enqueue loop, whichever is larger). Returns (device-resident result, host-input result) from ONE engine."""
     h_depth, h_rgb, d_depth, d_rgb, poses = frames
     n_frames = len(poses)
     p = vh.params_for_scene(sc, vox_size=cfg["vox_size"], trunc_margin=cfg["trunc"], max_depth=cfg["max_depth"], num_buckets=cfg["num_buckets"],
@@ -590,7 +598,7 @@ def sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_w
     eng.shard_connect(ids[0])
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
 
-    def one_pass(n):
+    def one_pass(n, host_inputs):
         for k in range(n):
             i = k % n_frames
             if rank != 0:
@@ -600,30 +608,34 @@ def sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_w
             else:
                 eng.integrate_sharded_device(d_depth[i].data_ptr(), d_rgb[i].data_ptr() if color else None, poses[i])
         eng.sync()
-    one_pass(n_warm)
-    eng.reset()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(stream)
-    one_pass(n_timed)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) * 1000.0
-    dist.barrier()
-    t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    mine = eng.stats()
-    u = torch.tensor([float(mine.voxel_updates_total), float(mine.allocated_blocks), float(mine.allocated_blocks)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(u[:2], op=dist.ReduceOp.SUM)
-    dist.all_reduce(u[2:], op=dist.ReduceOp.MAX)
-    out = {"frames_per_sec": n_timed / (ms / 1000.0), "voxel_updates_per_sec": float(u[0].item()) / (ms / 1000.0), "ms_per_frame": ms / n_timed, "frames": n_timed,
-           "allocated_blocks_all_shards": int(u[1].item()), "allocated_blocks_largest_shard": int(u[2].item()),
-           "last_frame_this_rank": {"ms_alloc": mine.ms_alloc, "ms_cull_list": mine.ms_cull, "ms_integrate": mine.ms_integrate, "ms_mc": mine.ms_mc}}
+
+    def measure(host_inputs, warm):
+        one_pass(warm, host_inputs)
+        eng.reset()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        one_pass(n_timed, host_inputs)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1000.0
+        dist.barrier()
+        t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        mine = eng.stats()
+        u = torch.tensor([float(mine.voxel_updates_total), float(mine.allocated_blocks), float(mine.allocated_blocks)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(u[:2], op=dist.ReduceOp.SUM)
+        dist.all_reduce(u[2:], op=dist.ReduceOp.MAX)
+        return {"frames_per_sec": n_timed / (ms / 1000.0), "voxel_updates_per_sec": float(u[0].item()) / (ms / 1000.0), "ms_per_frame": ms / n_timed, "frames": n_timed,
+                "allocated_blocks_all_shards": int(u[1].item()), "allocated_blocks_largest_shard": int(u[2].item()),
+                "last_frame_this_rank": {"ms_alloc": mine.ms_alloc, "ms_cull_list": mine.ms_cull, "ms_integrate": mine.ms_integrate, "ms_mc": mine.ms_mc}}
+    dev = measure(False, n_warm)
+    host = measure(True, min(n_warm, FRAMES_PER_STEP)) if with_host_inputs else None
     dist.barrier()
     eng.close()
-    return out
+    return dev, host
 
 
 def run_multi(args):
@@ -647,8 +659,7 @@ def run_multi(args):
     pool = args.pool_blocks or (3 << 20)
     frames = make_frames(torch, np, sc, n_frames, color, pinned=(rank == 0), device=(rank == 0))
     sampler = ClockSampler(local) if rank == 0 else None
-    main = sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_warm, n_timed, args.ray_steps, pool, frames, host_inputs=False)
-    e2e = sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, min(n_warm, FRAMES_PER_STEP), n_timed, args.ray_steps, pool, frames, host_inputs=True)
+    main, e2e = sharded_run(vh, torch, np, dist, cfg, sc, color, mc, rank, world, local, n_warm, n_timed, args.ray_steps, pool, frames)
     clocks = sampler.stop() if sampler else None
     side = {}
 
@@ -670,7 +681,7 @@ def run_multi(args):
             c = synth.CONFIGS["C2"]
             s2 = synth.make_scene("C2", color=color)
             f2 = make_frames(torch, np, s2, 100, color, pinned=(rank == 0), device=(rank == 0))
-            return sharded_run(vh, torch, np, dist, c, s2, color, mc, rank, world, local, 50, 100, 0, 3 << 20, f2, host_inputs=False)
+            return sharded_run(vh, torch, np, dist, c, s2, color, mc, rank, world, local, 50, 100, 0, 3 << 20, f2, with_host_inputs=False)[0]
         guarded("headline_c2_sharded", c2)
     # BASELINE config 5: one independent 640x480 / 5 mm sequence and map per GPU (phase-shifted trajectories), no data-path collective
     def replicas():

@@ -113,7 +113,7 @@ emu_engine* emu_create(const vh_params* p, int integrate_rev, int cull, int exac
   e->P = *p;
   StaticParams& S = e->S; memset(&S, 0, sizeof(S));
   derive_static_params(*p, S);
-  S.verify = 0; S.integrate_ctas_per_sm = 4; S.integrate_cull = cull; S.integrate_two_steps = 0; S.integrate_rev = integrate_rev;
+  S.verify = 0; S.integrate_ctas_per_sm = 4; S.integrate_cull = cull; S.integrate_parts = 2; S.integrate_rev = integrate_rev;
   S.mc_rev = mc_rev;
   e->rev = integrate_rev; e->alloc_rev = alloc_rev; e->weight_bound_bias = exact_color ? 1u << 20 : 0u;
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket, cap = 1024;      // vh_create

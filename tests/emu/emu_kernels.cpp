@@ -20,10 +20,10 @@ void run_direct_wide(void* p) {      // 64-bit voxel indices (pools beyond 2^23 
   IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
   vh::integrate_kernel_direct<C, V, DL, 3, true>(a->S, a->F, a->px, a->D);
 }
-template <bool C, bool V, bool DL, int NS>
+template <bool C, bool V, bool DL, int PARTS>
 void run_staged(void* p) {
   IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
-  vh::integrate_kernel_staged<C, V, DL, NS, 4>(a->S, a->F, a->px, a->D);
+  vh::integrate_kernel_staged<C, V, DL, PARTS, 4>(a->S, a->F, a->px, a->D);
 }
 void run_cull_list(void* p) {
   IntegrateArgs* a = static_cast<IntegrateArgs*>(p);
@@ -52,8 +52,11 @@ void emu_launch_integrate(const StaticParams& S, const FrameParams& F, const uin
   const bool delta = S.weight_bound <= 65536u;
   emu::run_grid(dim3(2), dim3(256), run_cull_list, &ia);
   if (rev == 2) {
-    void (*entry)(void*) = !color ? run_staged<false, false, false, 2> : delta ? run_staged<true, false, true, 2> : run_staged<true, false, false, 2>;
-    emu::run_grid(dim3(std::max(ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes(2));
+    // whole-block and half-block work items alternate between frames
+    const bool halves = (F.frame & 1u) != 0;
+    void (*entry)(void*) = halves ? (!color ? run_staged<false, false, false, 2> : delta ? run_staged<true, false, true, 2> : run_staged<true, false, false, 2>)
+                                  : (!color ? run_staged<false, false, false, 1> : delta ? run_staged<true, false, true, 1> : run_staged<true, false, false, 1>);
+    emu::run_grid(dim3(std::max(ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes(halves ? 2 : 1));
   } else {
     void (*entry)(void*) = !color ? run_direct<false, false, false, 3> : delta ? run_direct<true, false, true, 3> : run_direct<true, false, false, 3>;
     emu::run_grid(dim3(std::max(ctas, 1)), dim3(INT_THREADS), entry, &ia);
@@ -87,7 +90,7 @@ int emu_integrate(emu_integrate_io* io) {
   S.W = io->W; S.H = io->H; S.fx = io->fx; S.fy = io->fy; S.cx = io->cx; S.cy = io->cy; S.max_depth = io->max_depth;
   S.vox_size = io->vox_size; S.trunc = io->trunc; S.use_color = io->use_color;
   S.round_eps = 7.5e-7f * (float)std::max(io->W, io->H) + 2e-5f;    // vh_create, csrc/vh_engine.cu
-  S.byte_bias = 0x4B000000u; S.verify = io->verify; S.weight_bound = io->weight_bound; S.integrate_cull = io->cull; S.integrate_two_steps = io->two_steps;
+  S.byte_bias = 0x4B000000u; S.verify = io->verify; S.weight_bound = io->weight_bound; S.integrate_cull = io->cull; S.integrate_parts = io->two_steps ? 1 : 2;
   FrameParams F; memset(&F, 0, sizeof(F));
   memcpy(F.c2w, io->c2w, sizeof(F.c2w)); F.frame = io->frame;
 
@@ -119,12 +122,12 @@ int emu_integrate(emu_integrate_io* io) {
   void (*entry)(void*) = nullptr;
   emu::g_collectives = 0;
   emu::run_grid(dim3(2), dim3(256), run_cull_list, &ia);
-  if (io->variant == 2) {     // integrate_kernel_staged; two_steps selects the number of steps gated together
-#define PICK2(C, V, DL) (io->two_steps ? run_staged<C, V, DL, 2> : run_staged<C, V, DL, 1>)
+  if (io->variant == 2) {     // integrate_kernel_staged; two_steps = 1 selects whole-block work items, 0 = x-halves
+#define PICK2(C, V, DL) (io->two_steps ? run_staged<C, V, DL, 1> : run_staged<C, V, DL, 2>)
     if (io->verify) entry = !color ? PICK2(false, true, false) : delta ? PICK2(true, true, true) : PICK2(true, true, false);
     else entry = !color ? PICK2(false, false, false) : delta ? PICK2(true, false, true) : PICK2(true, false, false);
 #undef PICK2
-    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes(io->two_steps ? 2 : 1));
+    emu::run_grid(dim3(std::max(io->ctas, 1)), dim3(STG_THREADS), entry, &ia, integrate_staged_smem_bytes(io->two_steps ? 1 : 2));
   } else if (io->variant == 3) {      // integrate_kernel_direct with 64-bit voxel indices
     if (io->verify) entry = !color ? run_direct_wide<false, true, false> : delta ? run_direct_wide<true, true, true> : run_direct_wide<true, true, false>;
     else entry = !color ? run_direct_wide<false, false, false> : delta ? run_direct_wide<true, false, true> : run_direct_wide<true, false, false>;

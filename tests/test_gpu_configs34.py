@@ -1,8 +1,7 @@
 """GPU (B200): BASELINE configs 3 and 4 as parity cases (BASELINE.json: "the other configs are parity-test cases").
 Config 3: 1280x720, 4 mm voxels, 2^24-bucket hash, truncation 3 cm, full-map mesh extraction.
-Config 4: 10 m room centred on the origin (negative block coordinates), 2 mm voxels, truncation 1 cm.
-Written after the round's GPU time had run out (the same shapes pass under the CPU emulation of the kernel sources,
-tests/emu/headline_check.py); gated behind VH_TEST_REV1=1 until they have run once on a B200 (tools/gpu_rev1.sh)."""
+Config 4: 10 m room centred on the origin (negative block coordinates), 2 mm voxels, truncation 1 cm, at the reference's 100 ray
+steps and with the step cap scaled to the block size (1,100: the two-kernel allocation form). First green on B200 in profiles/r02a."""
 import os
 
 import numpy as np

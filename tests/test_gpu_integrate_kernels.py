@@ -11,13 +11,17 @@ from util import CASES, engine_params, load_golden
 pytestmark = pytest.mark.gpu
 
 
-# (VH_INTEGRATE_REV, CTAs per SM, steps gated together): 1 = direct (per-lane plane loads after the gate), 2 = staged (cp.async.bulk + mbarrier)
-@pytest.fixture(params=[("2", "4", "1"), ("2", "6", "0"), ("2", "5", "1"), ("1", "3", "0"), ("1", "4", "0")],
-                ids=["staged-4ctas-2steps", "staged-6ctas-1step", "staged-5ctas-2steps", "direct-3ctas", "direct-4ctas"])
+# (VH_INTEGRATE_REV, VH_INTEGRATE_PARTS, VH_INTEGRATE_CTAS): 2 = staged (cp.async.bulk + mbarrier; work items = whole blocks or x-halves,
+# chosen per frame by the host when not forced), 1 = direct (per-lane plane loads after the gate)
+@pytest.fixture(params=[("2", "2", "5"), ("2", "1", "4"), ("2", "2", "4"), ("2", "", ""), ("1", "", "3"), ("1", "", "4")],
+                ids=["staged-halves-5ctas", "staged-whole-4ctas", "staged-halves-4ctas", "staged-auto", "direct-3ctas", "direct-4ctas"])
 def kernel(request, monkeypatch):
     monkeypatch.setenv("VH_INTEGRATE_REV", request.param[0])
-    monkeypatch.setenv("VH_INTEGRATE_CTAS", request.param[1])
-    monkeypatch.setenv("VH_INTEGRATE_TWO_STEPS", request.param[2])
+    for name, v in (("VH_INTEGRATE_PARTS", request.param[1]), ("VH_INTEGRATE_CTAS", request.param[2])):
+        if v:
+            monkeypatch.setenv(name, v)
+        else:
+            monkeypatch.delenv(name, raising=False)
 
 
 @pytest.mark.parametrize("name", ["g8_color_holes", "g8_negative_coords"])

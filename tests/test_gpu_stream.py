@@ -1,6 +1,5 @@
-"""GPU (B200): the out-of-core tier through the C ABI (vh_far_blocks / vh_evict_blocks / vh_upload_blocks, csrc/vh_stream.cu).
-Written after the round's GPU time had run out; the kernels pass under CPU emulation (tests/test_emu_stream.py). Gated behind
-VH_TEST_REV1=1 until run once on a B200 (tools/gpu_rev1.sh)."""
+"""GPU (B200): the out-of-core tier through the C ABI (vh_far_blocks / vh_evict_blocks / vh_upload_blocks, csrc/vh_stream.cu):
+a run that streams blocks out and back in around every frame reproduces the oracle. First green on B200 in profiles/r02a."""
 import os
 
 import numpy as np

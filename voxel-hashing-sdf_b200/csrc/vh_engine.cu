@@ -147,7 +147,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
   { const char* v = getenv("VH_INTEGRATE_CTAS"); S.integrate_ctas_per_sm = (v && v[0] >= '3' && v[0] <= '6') ? v[0] - '0' : 0; }   // tuning knob; 0 = the kernel's default (direct 3 [or 4], staged 4 [or 5, 6])
   { const char* v = getenv("VH_INTEGRATE_EXACT_COLOR"); e->weight_bound_env = e->weight_bound_bias = (v && v[0] == '1') ? 1u << 20 : 0u; }
   { const char* v = getenv("VH_INTEGRATE_CULL"); S.integrate_cull = (v && v[0] == '0') ? 0 : 1; }
-  { const char* v = getenv("VH_INTEGRATE_TWO_STEPS"); S.integrate_two_steps = (v && v[0] == '0') ? 0 : 1; }
+  { const char* v = getenv("VH_INTEGRATE_PARTS"); e->integrate_parts_forced = (v && (v[0] == '1' || v[0] == '2')) ? v[0] - '0' : 0; S.integrate_parts = 2; }
   { const char* v = getenv("VH_INTEGRATE_REV"); S.integrate_rev = (v && v[0] == '1') ? 1 : 2; }      // 2 (default) = integrate_kernel_staged, 1 = integrate_kernel_direct
   { // allocation: 2 = ray_keys_kernel + insert_keys_kernel (sharded maps: rays split across the GPUs; long ray step caps), 0 = the one-kernel
     // form (a few us faster at the reference's 100-step cap on one GPU); VH_ALLOC_REV overrides
@@ -312,6 +312,17 @@ static int compact_arena(vh_engine* e, unsigned long long need) {
   return VH_OK;
 }
 
+// Work items of the staged integrate kernel for the coming launch: whole blocks when the last completed frame kept many blocks
+// after the whole-block discard (room-scale frames: ~470 k), x-halves otherwise (more items for the warps to share, smaller
+// staging buffers, 5 CTAs per SM). A performance choice only — results do not depend on it. The pinned status block is
+// refreshed by every frame, so it can be read without a sync.
+void pick_integrate_parts(vh_engine* e) {
+  if (e->integrate_parts_forced) { e->S.integrate_parts = e->integrate_parts_forced; return; }
+  const volatile DeviceStatus* hb = e->h_block;
+  const long long kept = (long long)hb->c.visible_count - (long long)hb->c.pad[1];
+  e->S.integrate_parts = kept >= 160000 ? 1 : 2;
+}
+
 // ---- frame pipeline -----------------------------------------------------------------------------
 int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEvent_t rgb_ready, const float* host_depth_mapped) {
   DeviceView& D = e->D;
@@ -340,6 +351,7 @@ int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEve
   launch_cull_list(e->S, e->F, D, e->num_sms, e->stream);          // integrate's work list: visible blocks minus the whole-block discards
   CK(cudaEventRecord(e->ev[2], e->stream));
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
+  pick_integrate_parts(e);
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->P.mc_per_frame)
@@ -590,6 +602,7 @@ int vh_stage_integrate(vh_engine* e, const float* d_depth, const uint8_t* d_rgb)
   launch_pack_frame(e->S, e->cur_depth, e->cur_rgb, px, e->D.tile_max, e->D.sched, nullptr, e->F.frame, e->stream);
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
   launch_cull_list(e->S, e->F, e->D, e->num_sms, e->stream);
+  pick_integrate_parts(e);
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, e->D, e->num_sms, e->stream);
   e->S.use_color = keep;
   int rc = enqueue_readback(e);

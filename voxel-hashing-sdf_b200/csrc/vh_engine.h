@@ -38,8 +38,8 @@ struct StaticParams {
   int verify;                     // debug: run fast and IEEE paths side by side and count disagreements
   uint32_t weight_bound;          // upper bound of any voxel weight after the coming integrate launch (= launches since reset)
   int integrate_cull;             // 1 (default): discard whole blocks behind everything seen in their footprint; 0: gate every voxel
-  int integrate_two_steps;        // staged kernel: 1 = gate two steps of a block together (8 pixel gathers in flight per lane), 0 = one step at a time
-  int integrate_ctas_per_sm;      // resident CTAs per SM the integrate kernel is compiled for (3 or 4; 0 = the kernel's default)
+  int integrate_parts;            // staged kernel: work items per block for the coming launch: 1 = whole blocks, 2 = x-halves (set per frame by the host)
+  int integrate_ctas_per_sm;      // resident CTAs per SM (tuning, VH_INTEGRATE_CTAS; 0 = the kernel's default: direct 3 [or 4], staged halves 5 [or 4])
   uint32_t byte_bias;             // 0x4B000000 (bits of 2^23), read from the parameter block by integrate_kernel_r1's byte -> float permutes
   int integrate_rev;              // 1: integrate_kernel_direct; 2: integrate_kernel_staged (planes through shared memory by bulk async copies)
   int alloc_rev;                  // 0: alloc_visible_kernel (one kernel, sequential DDA per ray); 2: ray_keys_kernel + insert_keys_kernel (DDA as a merge, keys routed to their owner)

@@ -59,6 +59,7 @@ struct vh_engine {
   uint32_t integrate_launches = 0;      // since the last reset: bounds every voxel weight
   uint32_t weight_bound_bias = 0;       // added to the weight bound: forces the general colour path (env VH_INTEGRATE_EXACT_COLOR=1, or non-integer uploaded weights)
   uint32_t weight_bound_env = 0;        // the environment's share of it (survives vh_reset)
+  int integrate_parts_forced = 0;       // env VH_INTEGRATE_PARTS (1 or 2); 0 = chosen per frame from the previous frame's work list (pick_integrate_parts)
   int mc_parity = 0;                    // which McQueueCtl slot the next marching-cubes launch uses
   uint32_t tombstones = 0;              // table entries released by vh_evict_blocks since the last rebuild (vh_stream.cu)
   // multi-GPU (vh_shard.cu)
@@ -79,6 +80,7 @@ int shard_barrier(vh_engine* e);                // vh_shard.cu: stream-ordered b
 int gather_block_triangles(vh_engine* e, const MeshBlocks& mb, vh_triangle* out, unsigned long long total, vh_triangle** d_keep);   // ordered soup of mb's blocks
 int weld_on_device(vh_engine* e, const vh_triangle* d_soup, unsigned long long T, std::vector<vh_vertex>& verts, std::vector<int32_t>& faces);   // vh_weld.cu
 extern "C" {
+void pick_integrate_parts(vh_engine* e);
 int enqueue_stages(vh_engine* e, bool do_alloc, cudaEvent_t depth_ready, cudaEvent_t rgb_ready, const float* host_depth_mapped);
 int enqueue_readback(vh_engine* e);
 int finish_sync(vh_engine* e);

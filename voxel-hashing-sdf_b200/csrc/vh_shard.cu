@@ -367,6 +367,7 @@ static int integrate_sharded_common(vh_engine* e, const float* depth, const uint
   launch_cull_list(e->S, e->F, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[2], e->stream));
   e->S.weight_bound = ++e->integrate_launches + e->weight_bound_bias;
+  pick_integrate_parts(e);
   launch_integrate(e->S, e->F, px, e->cur_rgb != nullptr, D, e->num_sms, e->stream);
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->P.mc_per_frame) {
