@@ -674,6 +674,9 @@ def run_multi(args):
     def single():
         if rank != 0:
             return None
+        need_gb = pool * (6144 if color else 4096) / 1e9
+        if need_gb > 150:
+            return {"not_run": f"a pool of {pool} blocks ({need_gb:.0f} GB) does not fit one GPU: this workload exists on the sharded map only"}
         return single_gpu_run(vh, torch, np, args.config, cfg, sc, color, mc, local, n_warm, n_timed, args.ray_steps, pool, frames=frames)
     guarded("single_gpu_same_run", single)
     if args.config != "C2":       # the headline config sharded the same way: a 0.2 ms frame, latency-bound
@@ -718,7 +721,7 @@ def run_multi(args):
             "roofline": None, "cpu_baseline": None, "clocks": clocks,
         }
         sg = side.get("single_gpu_same_run") or {}
-        if sg.get("per_frame"):
+        if isinstance(sg, dict) and sg.get("per_frame"):
             peak, peak_src = peak_hbm()
             pf = sg["per_frame"]
             b = 16.0 * pf["voxel_updates"] + 4.0 * W * H + 12.0 * pf["visible_blocks"] + ((8.0 * pf["voxel_updates"] + 3.0 * W * H) if color else 0.0)

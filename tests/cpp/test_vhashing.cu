@@ -71,6 +71,22 @@ __global__ void check_tags(const TableBase::HashEntry* e, int n, TableBase t, in
   if ((e[i].key.x & 1) != 0 || t[e[i]].tag != (float)(e[i].key.x + e[i].key.y + e[i].key.z)) atomicAdd(bad, 1);
 }
 
+// after a bulk allocation that overflowed the pool: device-side access to every requested key terminates (keys that got no
+// storage read as absent-with-error, not as "slot not yet published"), erase pushes stay inside the free-list, freed slots are reusable
+__global__ void touch_after_overflow(TableBase t, int n, int* reached, int* stored) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int3 k = make_int3(7000 + i, -3, i & 7);
+  const TableBase& ct = t;
+  const Payload& p = ct[k];                                        // const access: wait_slot must not spin on a pool-full entry
+  if (p.hits >= 0) atomicAdd(reached, 1);
+  if (t.find(k) != t.end() && t.find(k)->block_index >= 0) atomicAdd(stored, 1);
+}
+__global__ void erase_some(TableBase t, int n, int* erased) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && t.erase(make_int3(7000 + i, -3, i & 7))) atomicAdd(erased, 1);
+}
+
 #define REQUIRE(c) do { if (!(c)) { std::fprintf(stderr, "FAILED line %d: %s\n", __LINE__, #c); return 1; } } while (0)
 
 int main() {
@@ -128,6 +144,31 @@ int main() {
   bool threw = false;
   try { small.check(); } catch (const char* m) { threw = std::string(m) == "out of block memory"; }
   REQUIRE(threw);
+
+  // bulk allocation past the pool: the host call raises, and the table stays usable from device code
+  Table tiny(256, 4, 50, make_int3(999999, 999999, 999999));
+  std::vector<int3> over;
+  for (int i = 0; i < 120; i++) over.push_back(make_int3(7000 + i, -3, i & 7));
+  threw = false;
+  try { tiny.AllocKeys(over); } catch (const char* m) { threw = std::string(m) == "out of block memory"; }
+  REQUIRE(threw);
+  REQUIRE(tiny.size() == 50);                                        // key_heap lists exactly the blocks that got storage
+  cudaMemset(d, 0, 8 * sizeof(int));
+  touch_after_overflow<<<1, 128>>>(tiny, 120, d, d + 1);
+  REQUIRE(cudaDeviceSynchronize() == cudaSuccess);                   // no spin on SLOT_POOL_FULL entries
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  REQUIRE(h[0] == 120 && h[1] == 50);
+  erase_some<<<1, 128>>>(tiny, 120, d + 2);
+  REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  REQUIRE(h[2] == 120);                                              // every claimed entry goes, 50 slots return to the stack (inside its bounds)
+  int top = 0; cudaMemcpy(&top, tiny.view.free_top, sizeof(int), cudaMemcpyDeviceToHost);
+  REQUIRE(top == 50);
+  std::vector<int3> again;
+  for (int i = 0; i < 50; i++) again.push_back(make_int3(-40 - i, 2, 2));
+  REQUIRE(tiny.size() == 0);
+  try { tiny.AllocKeys(again); } catch (const char*) {}              // (the error flag is sticky: the call still reports the earlier overflow)
+  REQUIRE(tiny.size() == 50);                                        // the freed slots were handed out again
   std::printf("VHASHING_OK\n");
   return 0;
 }

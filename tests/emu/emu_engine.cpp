@@ -61,9 +61,9 @@ void run_insert_keys(void* p) { InsertArgs* a = static_cast<InsertArgs*>(p); ins
 struct McArgs { StaticParams S; uint32_t frame; DeviceView D; const int* list; const int* list_count; int full_map; unsigned long long* out_offset; int* out_count;
                 McWork* queue; McQueueCtl* ctl; McQueueCtl* ctl_next; const uint4* tables; };
 void run_filter_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<true>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
-void run_mesh_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
+void run_mesh_sharded(void* p) { McArgs* a = static_cast<McArgs*>(p); if (a->S.mc_rev) return mc_mesh_kernel<true, true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); mc_mesh_kernel<true, false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 void run_filter(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_filter_kernel<false>(a->S, a->frame, a->D, a->list, a->list_count, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl); }
-void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); mc_mesh_kernel<false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
+void run_mesh(void* p) { McArgs* a = static_cast<McArgs*>(p); if (a->S.mc_rev) return mc_mesh_kernel<false, true>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); mc_mesh_kernel<false, false>(a->S, a->frame, a->D, a->full_map, a->out_offset, a->out_count, a->queue, a->ctl, a->ctl_next, a->tables); }
 // test-only kernel: the step-by-step DDA (ray_march) and the merge formulation (merge_fill_keys) of the same tile of rays,
 // compared key by key; out[0] += mismatching steps, out[1] += steps compared, out[2] += non-empty keys
 struct MarchCmpArgs { StaticParams S; FrameParams F; const float* depth; int tiles_x; unsigned long long* out; };
@@ -212,7 +212,7 @@ int emu_phase_mc(emu_engine* e) {
     McArgs m{S, e->F.frame, D, D.visible, &D.counters->visible_count, 0, D.tri_offset, D.tri_count, D.mc_queue, ctl, ctl_next, e->tables.data()};
     const bool sharded = S.shard_count > 1 && D.peers;
     emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
-    emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
+    emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m, (size_t)MC_WARPS * TILE_PAD * sizeof(uint32_t));
   }
   return e->map_error | (e->engine_error << 8);
 }
@@ -240,7 +240,7 @@ long long emu_full_map_mc(emu_engine* e) {
   McArgs m{S, e->F.frame, D, e->full_list.data(), &count, 1, e->full_off.data(), e->full_cnt.data(), D.mc_queue, ctl, ctl_next, e->tables.data()};
   const bool sharded = S.shard_count > 1 && D.peers;
   emu::run_grid(dim3(3), dim3(256), sharded ? run_filter_sharded : run_filter, &m);
-  emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m);
+  emu::run_grid(dim3(3), dim3(MC_THREADS), sharded ? run_mesh_sharded : run_mesh, &m, (size_t)MC_WARPS * TILE_PAD * sizeof(uint32_t));
   long long t = 0;
   for (int i = 0; i < nb; i++) t += e->full_cnt[i];
   e->full_valid = 1;

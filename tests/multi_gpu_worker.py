@@ -21,6 +21,7 @@ MODES = [   # label, environment, frames in flight (no sync between frames, devi
     ("pull+replicated-rays", {"VH_ALLOC_REV": "0"}, False),
     ("nccl-broadcast+split-rays", {"VH_ALLOC_REV": "2", "VH_SHARD_BCAST": "nccl"}, True),
     ("pull+split-rays+direct-integrate", {"VH_ALLOC_REV": "2", "VH_INTEGRATE_REV": "1"}, True),
+    ("pull+split-rays+mc-colour-tile", {"VH_ALLOC_REV": "2", "VH_MC_COLOR_TILE": "1"}, True),
 ]
 
 

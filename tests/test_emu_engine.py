@@ -50,8 +50,8 @@ SMALL = dict(width=160, height=120, room=(4.0, 3.0, 2.5), n_frames=60, spheres=(
 CASE = dict(scene=dict(color=True), vpb=8, vox_size=0.04, trunc=0.2, max_depth=3.0)
 
 
-# kernel revisions (integrate, allocation, marching cubes): 0 = shipped defaults, 1 = opt-in (VH_INTEGRATE_REV / VH_ALLOC_REV / VH_MC_REV = 1)
-@pytest.mark.parametrize("rev,alloc_rev,mc_rev", [(1, 0, 0), (2, 0, 0), (1, 2, 0), (2, 2, 0)])
+# (integrate kernel: 1 direct, 2 staged; allocation: 0 one kernel, 2 keys + insert; marching-cubes mesh kernel: 1 = colour tile through shared memory)
+@pytest.mark.parametrize("rev,alloc_rev,mc_rev", [(1, 0, 0), (2, 0, 1), (1, 2, 1), (2, 2, 0)])
 def test_emulated_engine_matches_oracle(vh, ob, synth, rev, alloc_rev, mc_rev):
     nblocks, ntris = run_pair(vh, ob, synth, SMALL, CASE, frames=3, rev=rev, alloc_rev=alloc_rev, mc_rev=mc_rev, num_buckets=1 << 12,
                               pool_blocks=1 << 12, tri_arena_bytes=8 << 20)
@@ -240,7 +240,7 @@ def _random_pose_scene(synth, seed, **kw):
     return RandomPoses(**kw)
 
 
-@pytest.mark.parametrize("seed,revs", [(1, (1, 0, 0)), (2, (1, 2, 0)), (3, (2, 0, 0)), (4, (1, 0, 0)), (5, (2, 2, 0)), (6, (1, 2, 0))])
+@pytest.mark.parametrize("seed,revs", [(1, (1, 0, 0)), (2, (1, 2, 1)), (3, (2, 0, 1)), (4, (1, 0, 0)), (5, (2, 2, 0)), (6, (1, 2, 1))])
 def test_emulated_engine_random_rigid_poses(vh, ob, synth, seed, revs):
     """odd image size (not a multiple of the 16-pixel tiles or the 10-pixel ray stride), off-centre principal point,
     random rigid poses; three frames that overlap only by chance"""
@@ -266,7 +266,7 @@ def test_emulated_engine_random_rigid_poses(vh, ob, synth, seed, revs):
         assert len(keys) > 100
 
 
-@pytest.mark.parametrize("mc_rev", [0])
+@pytest.mark.parametrize("mc_rev", [0, 1])
 def test_emulated_full_map_extraction(vh, ob, synth, mc_rev):
     """VH_MESH_FULL_MAP: every allocated block re-meshed against the whole map (a corner counts if its block is allocated at
     all) — list_all_blocks_kernel + both marching-cubes kernels with full_map = 1 — against the oracle's full-map pass;
@@ -302,6 +302,6 @@ def test_emulated_engine_under_another_thread_order():
     for order in ("reverse", "random:3"):
         env = dict(os.environ, VH_EMU_ORDER=order, VH_EMU_NO_REBUILD="1")
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_engine.py"), "-x", "-q", "-p", "no:cacheprovider",
-                            "-k", "matches_oracle and 2-2-0 or sharded and 3-1-2 or merge_equals"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+                            "-k", "matches_oracle and 2-0-1 or sharded and 3-1-2 or merge_equals"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
         assert r.returncode == 0, f"VH_EMU_ORDER={order}:\n{r.stdout[-2000:]}"
         assert "3 passed" in r.stdout, r.stdout[-500:]

@@ -32,6 +32,8 @@ int fail(int code, const char* fmt, ...) {
 }
 extern "C" int vh_set_error_(int code, const char* msg) { g_err = msg ? msg : ""; return code; }
 
+constexpr int VH_MC_COLOR_TILE_DEFAULT = 0;      // set from the measurement in profiles/r02final (both settings run in the GPU test suite)
+
 // ---- frame constants on the host: derive_frame_params (vh_params_host.h)
 void setup_frame(vh_engine* e, const float* c2w) {
   derive_frame_params(e->P, e->S, c2w, e->F);
@@ -154,7 +156,7 @@ int vh_create(const vh_params* p, vh_engine** out) {
     const char* v = getenv("VH_ALLOC_REV");
     S.alloc_rev = (v && (v[0] == '0' || v[0] == '2')) ? v[0] - '0' : ((p->shard_count > 1 || p->max_ray_steps > 256) ? 2 : 0);
   }
-  S.mc_rev = 0;      // (unused: the marching-cubes revisions of round 1 were measured and merged)
+  { const char* v = getenv("VH_MC_COLOR_TILE"); S.mc_rev = v ? (v[0] == '1' ? 1 : 0) : VH_MC_COLOR_TILE_DEFAULT; }   // mesh kernel: colour tile through shared memory
   static_assert(sizeof(StaticParams) % 16 == 0, "keep the FrameParams behind StaticParams 16-byte aligned in the kernels' parameter blocks");
 
   uint64_t want = (uint64_t)p->num_buckets * (uint64_t)p->entries_per_bucket;
@@ -173,7 +175,8 @@ int vh_create(const vh_params* p, vh_engine** out) {
 #define ALLOC(ptr, bytes)                                                                                           \
   do {                                                                                                              \
     cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                                           \
-    if (_e != cudaSuccess) { int rc = fail(VH_ERR_CUDA, "CUDA Error: cudaMalloc(%zu bytes) for %s: %s", (size_t)(bytes), #ptr, cudaGetErrorString(_e)); free_engine(e); return rc; } \
+    if (_e != cudaSuccess) { cudaGetLastError(); /* not sticky: keep it from surfacing in a later, unrelated call */ \
+      int rc = fail(VH_ERR_CUDA, "CUDA Error: cudaMalloc(%zu bytes) for %s: %s", (size_t)(bytes), #ptr, cudaGetErrorString(_e)); free_engine(e); return rc; } \
   } while (0)
   ALLOC(D.map.keys, cap * sizeof(u64));
   ALLOC(D.map.slots, cap * sizeof(int));

@@ -43,7 +43,7 @@ struct StaticParams {
   uint32_t byte_bias;             // 0x4B000000 (bits of 2^23), read from the parameter block by integrate_kernel_r1's byte -> float permutes
   int integrate_rev;              // 1: integrate_kernel_direct; 2: integrate_kernel_staged (planes through shared memory by bulk async copies)
   int alloc_rev;                  // 0: alloc_visible_kernel (one kernel, sequential DDA per ray); 2: ray_keys_kernel + insert_keys_kernel (DDA as a merge, keys routed to their owner)
-  int mc_rev;                     // 0 (default); 1: the mesh kernel's emit pass issues a triangle's six colour gathers before interpolating (VH_MC_REV=1)
+  int mc_rev;                     // marching-cubes mesh kernel: 1 = the block's colour tile is staged in shared memory by cp.async while pass 1 runs (VH_MC_COLOR_TILE)
   // sizeof(StaticParams) stays a multiple of 16: the FrameParams that follows it in every kernel's parameter block keeps its
   // 16-byte alignment, so its pose is still fetched with 128-bit constant loads (add fields four ints at a time)
 };

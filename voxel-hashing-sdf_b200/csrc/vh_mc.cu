@@ -94,6 +94,7 @@ constexpr int TILE = 9, TILE_PAD = 736;   // 9^3 = 729 cells, padded
 
 struct McBlock {            // per-warp context of the block being meshed
   const float* tile;        // 9^3 sdf tile in shared memory
+  const uint32_t* ctile;    // colour tile in shared memory (CTILE kernels): [512] the block's own voxels in plane order, [512 + c] halo cell c
   const int* nb_slot;       // pool slots of the 8 corner blocks (bit0 +x, bit1 +y, bit2 +z), -1 = absent
   const int* nb_owner;      // multi-GPU: shard that holds each corner block (its planes are read through D.peers)
   int bx, by, bz;
@@ -103,8 +104,43 @@ struct McBlock {            // per-warp context of the block being meshed
 // the two colour gathers) and edge_finish (positions, VertexInterp). A triangle's three fetches are issued before the first
 // finish, so its six colour gathers are all in flight before the first interpolation consumes one (measured on B200 against
 // fetch-and-interpolate one vertex at a time: 0.069 -> 0.066 ms per frame, profiles/r02a).
+// asynchronous global -> shared copies without registers (LDGSTS): the colour tile travels while pass 1 runs
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+#ifdef VH_HOST_EMU
+  memcpy(dst_smem, src, 16);
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+#ifdef VH_HOST_EMU
+  memcpy(dst_smem, src, 4);
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef VH_HOST_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef VH_HOST_EMU
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// colour of the tile cell (x, y, z), 0..8 each, out of the staged colour tile
+__device__ __forceinline__ uint32_t ctile_color(const uint32_t* ctile, int x, int y, int z) {
+  int i;
+  if (((x | y | z) & 8) == 0) i = x * 64 + y * 8 + z;
+  else if (x == 8) i = 512 + y * 9 + z;
+  else if (y == 8) i = 512 + 81 + x * 9 + z;
+  else i = 512 + 153 + x * 8 + y;
+  return ctile[i] & 0xFFFFFFu;
+}
+
 struct EdgeFetch { int a_pos, b_pos; float va, vb; uint32_t ca, cb; };   // positions packed x | y << 8 | z << 16 (tile coordinates 0..8)
-template <bool SHARDED>
+template <bool SHARDED, bool CTILE>
 __device__ __forceinline__ EdgeFetch edge_fetch(const McBlock& B, const DeviceView& D, int lx, int ly, int lz, int e, bool color) {
   const int a = e < 8 ? e : e - 8;
   const int b = e < 4 ? ((e + 1) & 3) : (e < 8 ? 4 + ((e - 3) & 3) : e - 4);
@@ -113,7 +149,9 @@ __device__ __forceinline__ EdgeFetch edge_fetch(const McBlock& B, const DeviceVi
   EdgeFetch f;
   f.a_pos = ax | (ay << 8) | (az << 16); f.b_pos = qx | (qy << 8) | (qz << 16);
   f.ca = 0; f.cb = 0;
-  if (color) {
+  if (color && CTILE) {
+    f.ca = ctile_color(B.ctile, ax, ay, az); f.cb = ctile_color(B.ctile, qx, qy, qz);
+  } else if (color) {
     const int ma = (ax >> 3) | ((ay >> 3) << 1) | ((az >> 3) << 2), mb = (qx >> 3) | ((qy >> 3) << 1) | ((qz >> 3) << 2);
     const int sa = B.nb_slot[ma], sb = B.nb_slot[mb];
     const uchar4* rgb_a = SHARDED ? D.peers->v[B.nb_owner[ma]].rgb : D.rgb;
@@ -146,9 +184,9 @@ __device__ __forceinline__ int cube_index(const float* tile, int lx, int ly, int
 // B.nb_slot[0..8) holds the pool slots of the block and its seven upper neighbours (-1 = absent), `present` the same as bits.
 // cube_cache keeps the cube index of every voxel that has triangles (one byte per voxel per warp) so that the emit pass does not
 // rebuild it from eight shared-memory reads per candidate triangle.
-template <bool SHARDED>
+template <bool SHARDED, bool CTILE>
 __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D, const int slot, const unsigned present, const int (&halo)[7],
-                                          float* tile, unsigned short* wlist, unsigned char* cube_cache, const signed char* s_tri, const unsigned char* s_ntri,
+                                          float* tile, uint32_t* ctile, unsigned short* wlist, unsigned char* cube_cache, const signed char* s_tri, const unsigned char* s_ntri,
                                           const bool color, unsigned long long* __restrict__ out_offset, int* __restrict__ out_count,
                                           const int lane, const uint32_t frame) {
     // okbits bit q: every corner block a voxel with boundary mask q touches is present
@@ -193,6 +231,25 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
       return 0;
     }
     __syncwarp();
+    // CTILE: the block's colours (2 KB, coalesced) and the 217 halo colours start travelling into shared memory now, without
+    // registers, and arrive while pass 1 runs; pass 2 then interpolates colours out of shared memory instead of six dependent
+    // global gathers per triangle (the mesh kernel's top stall, profiles/r02_ncu/ncu_source_mcmesh.txt)
+    if (CTILE && color) {
+      const uchar4* own = (SHARDED ? D.peers->v[B.nb_owner[0]].rgb : D.rgb) + (size_t)slot * BLOCK_VOX;
+#pragma unroll
+      for (int j = 0; j < 4; j++) cp_async_16(ctile + (j * 32 + lane) * 4, own + (j * 32 + lane) * 4);
+#pragma unroll
+      for (int h = 0; h < 7; h++) {
+        const int d = halo[h];
+        if (d >= 0) {
+          const int s = B.nb_slot[(d >> 9) & 7];
+          const uchar4* plane = SHARDED ? D.peers->v[B.nb_owner[(d >> 9) & 7]].rgb : D.rgb;
+          if (s >= 0) cp_async_4(ctile + 512 + h * 32 + lane, plane + (size_t)s * BLOCK_VOX + (d & 511));
+          else ctile[512 + h * 32 + lane] = 0u;
+        }
+      }
+      cp_async_commit();
+    }
 
     // pass 1 (count): list the candidate triangles of the block as (tid << 3 | k) in the reference's slot order.
     // Reference thread -> voxel mapping (tsdf.cu:903-906) for VPB = 8: tid = j*32 + lane -> x = tid >> 6,
@@ -231,6 +288,7 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
       fits = __shfl_sync(0xffffffffu, fits, 0);
     }
 
+    if (CTILE && color) { cp_async_wait_all(); __syncwarp(); }
     // pass 2 (emit): one candidate triangle per lane; survivors of the degenerate rule are written compactly, in order
     int written = 0;
     if (nlist > 0 && fits) {
@@ -243,8 +301,8 @@ __device__ __forceinline__ int mesh_block(const McBlock& B, const DeviceView& D,
           const int t = item >> 3, k = item & 7;
           const int lx = t >> 6, ly = ((t >> 3) - B.bz) & 7, lz = t & 7;
           const signed char* row = s_tri + (int)cube_cache[t] * 16 + 3 * k;
-          const EdgeFetch f0 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[0], color), f1 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[1], color),
-                          f2 = edge_fetch<SHARDED>(B, D, lx, ly, lz, row[2], color);
+          const EdgeFetch f0 = edge_fetch<SHARDED, CTILE>(B, D, lx, ly, lz, row[0], color), f1 = edge_fetch<SHARDED, CTILE>(B, D, lx, ly, lz, row[1], color),
+                          f2 = edge_fetch<SHARDED, CTILE>(B, D, lx, ly, lz, row[2], color);
           p0 = edge_finish(B, f0, color); p1 = edge_finish(B, f1, color); p2 = edge_finish(B, f2, color);
           valid = !(same_pos(p0, p1) || same_pos(p1, p2));                       // p0 == p2 is never tested (Q5, tsdf.cu:1055-1057)
         }
@@ -342,7 +400,7 @@ mc_filter_kernel(const StaticParams S, const uint32_t frame, const DeviceView D,
 // Persistent warps pull blocks off the work queue (one atomicAdd per block) and mesh them: perfect balance whatever the
 // spatial clustering of surface blocks. The last thing the kernel does is clear the OTHER queue-control slot, which the
 // next launch pair will use (the two slots alternate, so no memset node is needed per frame).
-template <bool SHARDED>
+template <bool SHARDED, bool CTILE>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, const int full_map, unsigned long long* __restrict__ out_offset,
                int* __restrict__ out_count, const McWork* __restrict__ queue, McQueueCtl* __restrict__ ctl, McQueueCtl* __restrict__ ctl_next,
@@ -354,6 +412,11 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
   __shared__ __align__(16) signed char s_tri[256 * 16];
   __shared__ __align__(16) unsigned char s_ntri[256];
   __shared__ unsigned char s_cube[MC_WARPS][BLOCK_VOX];        // cube index of the voxels that have triangles
+#ifdef VH_HOST_EMU
+  uint32_t* dyn_ctile = reinterpret_cast<uint32_t*>(emu::g_cta->dyn_smem);
+#else
+  extern __shared__ __align__(16) uint32_t dyn_ctile[];        // CTILE: [MC_WARPS][TILE_PAD] colour tiles (dynamic: with it the CTA holds more than 48 KB)
+#endif
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int total = ctl->count;
@@ -381,20 +444,22 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
     halo[h] = c < 217 ? ((((tx * TILE + ty) * TILE + tz) << 12) | (m << 9) | ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))) : -1;
   }
 
+  // queue items are popped one ahead: the atomic's round trip overlaps the block being meshed
+  int idx_next = 0;
+  if (lane == 0) idx_next = atomicAdd(&ctl->head, 1);
   for (;;) {
-    int idx = 0;
-    if (lane == 0) idx = atomicAdd(&ctl->head, 1);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
+    const int idx = __shfl_sync(0xffffffffu, idx_next, 0);
     if (idx >= total) break;
+    if (lane == 0) idx_next = atomicAdd(&ctl->head, 1);
     const McWork* w = queue + idx;
     McBlock C;
-    C.bx = w->bx; C.by = w->by; C.bz = w->bz; C.tile = tile; C.nb_slot = s_nb[wid]; C.nb_owner = s_nbo[wid];
+    C.bx = w->bx; C.by = w->by; C.bz = w->bz; C.tile = tile; C.ctile = CTILE ? dyn_ctile + wid * TILE_PAD : nullptr; C.nb_slot = s_nb[wid]; C.nb_owner = s_nbo[wid];
     const int cur_slot = w->slot;
     const unsigned present = w->present;
-    __syncwarp();                              // previous block's readers of s_nb / tile / list are done
+    __syncwarp();                              // previous block's readers of s_nb / tile / colour tile / list are done
     if (lane < 8) { s_nb[wid][lane] = w->nb[lane]; s_nbo[wid][lane] = SHARDED ? (int)w->owner[lane] : 0; }
     __syncwarp();
-    my_tris += (unsigned long long)mesh_block<SHARDED>(C, D, cur_slot, present, halo, tile, s_list[wid], s_cube[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
+    my_tris += (unsigned long long)mesh_block<SHARDED, CTILE>(C, D, cur_slot, present, halo, tile, CTILE ? dyn_ctile + wid * TILE_PAD : nullptr, s_list[wid], s_cube[wid], s_tri, s_ntri, color, out_offset, out_count, lane, frame);
   }
   if (lane == 0 && my_tris && !full_map) atomicAdd(&D.counters->triangles, my_tris);
 }
@@ -413,13 +478,21 @@ void launch_marching_cubes(const StaticParams& S, const FrameParams& F, const De
   static const int mesh_ctas = [] { const char* v = getenv("VH_MC_MESH_CTAS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 6 ? n : 5; }();
   const int fgrid = num_sms * filter_ctas;
   const int mgrid = num_sms * mesh_ctas;         // 5 CTAs of 4 warps fit an SM (36.7 KB of shared memory each)
-  if (S.shard_count > 1 && D.peers) {
+  // colour tile through shared memory (VH_MC_COLOR_TILE, see mesh_block): 11.5 KB of dynamic shared memory more, 4 instead of 5 CTAs per SM
+  const bool use_ctile = S.mc_rev == 1 && S.use_color;
+  const size_t dyn = use_ctile ? (size_t)MC_WARPS * TILE_PAD * sizeof(uint32_t) : 0;
+  const bool sharded = S.shard_count > 1 && D.peers;
+#define VH_MESH(SH, CT) do { \
+    if (CT) { static bool done[16] = {}; if (!done[dev & 15]) { cudaFuncSetAttribute(mc_mesh_kernel<SH, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); done[dev & 15] = true; } } \
+    mc_mesh_kernel<SH, CT><<<(CT ? num_sms * 4 : mgrid), MC_THREADS, dyn, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]); } while (0)
+  if (sharded) {
     mc_filter_kernel<true><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    mc_mesh_kernel<true><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    if (use_ctile) VH_MESH(true, true); else VH_MESH(true, false);
   } else {
     mc_filter_kernel<false><<<fgrid, 256, 0, st>>>(S, F.frame, D, list, list_count, full_map, out_offset, out_count, D.mc_queue, ctl);
-    mc_mesh_kernel<false><<<mgrid, MC_THREADS, 0, st>>>(S, F.frame, D, full_map, out_offset, out_count, D.mc_queue, ctl, ctl_next, g_tables_dev[dev & 15]);
+    if (use_ctile) VH_MESH(false, true); else VH_MESH(false, false);
   }
+#undef VH_MESH
 }
 #endif  // !VH_HOST_EMU
 
