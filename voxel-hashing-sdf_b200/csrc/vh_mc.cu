@@ -444,13 +444,13 @@ mc_mesh_kernel(const StaticParams S, const uint32_t frame, const DeviceView D, c
     halo[h] = c < 217 ? ((((tx * TILE + ty) * TILE + tz) << 12) | (m << 9) | ((tx & 7) * 64 + (ty & 7) * 8 + (tz & 7))) : -1;
   }
 
-  // queue items are popped one ahead: the atomic's round trip overlaps the block being meshed
-  int idx_next = 0;
-  if (lane == 0) idx_next = atomicAdd(&ctl->head, 1);
+  // (Popping the next queue item ahead of the block in flight was measured and dropped: with ~2 blocks per warp a warp that holds
+  //  its next item while it meshes keeps it from an idle warp — 0.059 -> 0.073 ms per frame on config 2, profiles/r02final.)
   for (;;) {
-    const int idx = __shfl_sync(0xffffffffu, idx_next, 0);
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&ctl->head, 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= total) break;
-    if (lane == 0) idx_next = atomicAdd(&ctl->head, 1);
     const McWork* w = queue + idx;
     McBlock C;
     C.bx = w->bx; C.by = w->by; C.bz = w->bz; C.tile = tile; C.ctile = CTILE ? dyn_ctile + wid * TILE_PAD : nullptr; C.nb_slot = s_nb[wid]; C.nb_owner = s_nbo[wid];
