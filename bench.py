@@ -43,7 +43,6 @@ sys.path.insert(0, ROOT)
 FRAMES_PER_STEP = 50
 METRIC = "depth_frames_per_sec_640x480_5mm"
 UNIT = "frames/s"
-SHARDED_TIMEOUT_S = 300     # bench.py --gpus N>1: upper bound for the optional sharded-map section
 
 
 def parse():

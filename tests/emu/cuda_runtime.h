@@ -196,6 +196,7 @@ static inline void __threadfence_system() {}
 
 // ---- atomics (nothing runs concurrently) ----------------------------------------------------------------------------
 template <typename T, typename U> static inline T atomicAdd(T* p, U v) { const T o = *p; *p = (T)(o + (T)v); return o; }
+template <typename T, typename U> static inline T atomicAdd_system(T* p, U v) { return atomicAdd(p, v); }
 template <typename T, typename U> static inline T atomicSub(T* p, U v) { const T o = *p; *p = (T)(o - (T)v); return o; }
 template <typename T, typename U> static inline T atomicOr(T* p, U v) { const T o = *p; *p = (T)(o | (T)v); return o; }
 template <typename T, typename U> static inline T atomicAnd(T* p, U v) { const T o = *p; *p = (T)(o & (T)v); return o; }

@@ -1,5 +1,6 @@
-"""GPU (>= 2 B200s): one map sharded by block hash over the GPUs, NCCL frame broadcast, peer-memory marching-cubes halos,
-mesh gather — the union must equal the single-GPU engine bit for bit. Skipped on a single-GPU box."""
+"""GPU (>= 2 B200s): one map sharded by block hash over the GPUs — frames pulled out of rank 0's ring by the copy engines (or NCCL
+broadcast), rays split across the GPUs with keys routed to their owners' inboxes, peer-memory marching-cubes halos, mesh gather — in six
+modes (tests/multi_gpu_worker.py); the union must equal the single-GPU engine bit for bit. Skipped on a single-GPU box."""
 import os
 import subprocess
 import sys

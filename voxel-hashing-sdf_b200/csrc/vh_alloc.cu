@@ -375,7 +375,7 @@ ray_keys_kernel(const __grid_constant__ StaticParams S, const __grid_constant__ 
   // one reservation per owner per CTA, in the owner's inbox (a peer's: a remote atomic over NVLink)
   if (tid < MAX_SHARDS && s_cnt[tid] > 0) {
     int* cnt = routed ? D.peers->v[tid].inbox_count : D.inbox_count;
-    s_base[tid] = atomicAdd(&cnt[parity], s_cnt[tid]);
+    s_base[tid] = routed ? atomicAdd_system(&cnt[parity], s_cnt[tid]) : atomicAdd(&cnt[parity], s_cnt[tid]);   // a peer's counter: system scope
   }
   __syncthreads();
   for (int i = tid; i < nkeys; i += KEYS_THREADS) {
