@@ -91,7 +91,8 @@ def config_dict(args, cfg, sc, world):
         "per_frame_path": "upload + allocate + integrate" + ("" if args.no_mc else " + working-set marching cubes"),
         "color": not args.no_color,
         "multi_gpu": "one independent sequence+map per GPU (config 5 style), no collective on the data path" if world > 1 else "single map",
-        "l2": "inputs larger than L2: every frame is a distinct 1.2 MB depth (+0.9 MB rgb) image and touches a ~280 MB voxel working set (L2 = 126 MB)",
+        "l2": "inputs larger than L2: every frame is a distinct image and touches a voxel working set of "
+              + {"C1": "~0.45 GB", "C2": "~0.28-0.45 GB", "C3": "~0.3 GB", "C4": "~7 GB (1.2 M visible blocks)"}.get(args.config, "hundreds of MB") + " (L2 = 126 MB)",
         # run-time switches in effect; empty = the shipped defaults
         "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("VH_") and k != "VH_TEST_REV1"},
     }
