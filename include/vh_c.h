@@ -155,12 +155,14 @@ VH_API int vh_weld_mesh(vh_engine* e, int mode, vh_vertex* verts, uint64_t vcap,
  * (shard_count = number of GPUs); a block belongs to shard
  * vh_owner_of_block(x, y, z, shard_count, shard_group): ownership is hashed per cube of shard_group^3 blocks. Rank 0 obtains an
  * NCCL id (vh_shard_unique_id) and passes it to the other processes by any means; every rank then calls
- * vh_shard_connect (collective): NCCL communicator + CUDA-IPC mappings of the peers' tables and voxel planes, which the
- * marching-cubes kernel reads directly over NVLink for block-border neighbours.
- * vh_integrate_sharded (collective, same order on every rank): {pose, depth, rgb} are broadcast from rank 0 with NCCL on
- * the engine's stream, every GPU allocates, integrates and meshes its own blocks. depth / rgb are read on rank 0 only;
- * c2w may be NULL on the other ranks (they then take the broadcast pose at the price of a stream sync per frame).
- * Asynchronous like vh_integrate_async: call vh_sync before reading results.
+ * vh_shard_connect (collective): NCCL communicator + CUDA-IPC mappings of the peers' tables, voxel planes, key inboxes, flag words and
+ * rank 0's frame ring, which the kernels address directly over NVLink.
+ * vh_integrate_sharded (collective, same order on every rank): rank 0 puts {pose, depth, rgb} into its frame ring and every other GPU's
+ * copy engine pulls it over NVLink one frame ahead (env VH_SHARD_BCAST=nccl: ncclBroadcast instead); the rays are split across the
+ * GPUs and every block key travels to its owner's inbox; every GPU allocates, integrates and meshes its own blocks, reading
+ * marching-cubes halos out of the owner's memory. depth / rgb are read on rank 0 only (vh_integrate_sharded_device: device pointers);
+ * c2w may be NULL on the other ranks (they then take the pose out of the frame at the price of a stream sync per frame).
+ * Asynchronous like vh_integrate_async: call vh_sync before reading results. vh_reset of a sharded engine is collective.
  * vh_shard_gather_mesh (collective): the whole map's triangle soup on rank 0, merged in tsdf2mesh order, equal to the
  * single-GPU result; other ranks get *n = 0. vh_shard_stats (collective): group-wide sums of the last frame's counters. */
 #define VH_NCCL_ID_BYTES 128

@@ -2,7 +2,7 @@
 """BASELINE-shaped frames WITHOUT a GPU: the engine's kernel sources under CPU emulation (tests/emu) against the oracle, bit for bit —
 visible set, voxel updates and triangle count per frame, then every voxel, the ordered triangle soup and the full-map mesh.
 About one minute per 640x480 frame. Examples:
-  tests/emu/headline_check.py --config C2 --frames 3 --revs 1 1 1       (the opt-in kernel revisions at the headline shape)
+  tests/emu/headline_check.py --config C2 --frames 3 --revs 2 2 1       (revs: integrate 1 direct / 2 staged, allocation 0 one kernel / 2 keys + insert, MC 1 = colour tile)
   tests/emu/headline_check.py --config C3 --frames 1                   (1280x720, 4 mm, 2^24 buckets)
   tests/emu/headline_check.py --config C4 --frames 1 --ranks 4         (room scale, 2 mm, one map sharded over 4 emulated ranks)"""
 import argparse
