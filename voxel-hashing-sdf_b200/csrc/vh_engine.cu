@@ -252,7 +252,14 @@ int vh_reset(vh_engine* e) {
   CK(cudaSetDevice(e->P.device));
   if (e->shard) { int rc = shard_barrier(e); if (rc != VH_OK) return rc; }     // sharded map (collective): no peer is still meshing against these voxels
   CK(cudaStreamSynchronize(e->stream));
-  return reset_map(e);
+  int rc = reset_map(e);
+  if (rc != VH_OK || !e->shard) return rc;
+  // ... and nobody starts the next frame before EVERY GPU has finished resetting: a fast peer's ray_keys_kernel would otherwise
+  // add keys to this GPU's inbox (and bump its counter) ahead of the memsets above
+  rc = shard_barrier(e);
+  if (rc != VH_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return VH_OK;
 }
 
 // ---- triangle arena maintenance -----------------------------------------------------------------
